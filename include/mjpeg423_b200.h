@@ -1,0 +1,184 @@
+/*
+ * mjpeg423_b200.h -- C-ABI of the B200-native MJPEG423 decode hot path (libmjpeg423_b200.so).
+ *
+ * Reference citations: LIB = /root/reference/core0/software/common/libs/mjpeg423,
+ *                      C0  = /root/reference/core0/software.
+ *
+ * Three groups of entry points:
+ *   1. the reference LIBRARY seam   -- the exact symbols of LIB/decoder/mjpeg423_decoder.h:14-17 and the
+ *      tables of LIB/common/mjpeg423_types.h:64-66, so a caller of the reference links against this
+ *      library unchanged (drop-in shims: every call runs the CUDA path on a batch of one);
+ *   2. the reference ACCELERATOR seam -- the submit/collect/poll calls of
+ *      C0/idct_ycbcr_to_rgb_accel.h:13-22 (the FPGA IDCT + colour block this library replaces);
+ *   3. the THROUGHPUT API (additive) -- batched frame-range decode of an in-memory .mpg, mirroring the
+ *      loop body LIB/decoder/mjpeg423_decoder.c:90-124, with device-resident and host-buffer variants.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Group 1/2 functions return void/int exactly
+ * as the reference does (1 = success for init, C0/idct_ycbcr_to_rgb_accel.c:39-59).  Group 3 functions
+ * return 0 on success or a negative MJPEG423_E_* code and never call exit().  The caller owns every
+ * buffer passed in.  There is NO CPU fallback: without a CUDA device every entry point fails (group 3:
+ * MJPEG423_E_CUDA; group 1/2: message on stderr + abort(), the library analogue of the reference's
+ * error_and_exit, LIB/common/util.c:13-16).
+ */
+#ifndef MJPEG423_B200_H
+#define MJPEG423_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- types: LIB/common/mjpeg423_types.h:22-61 ---------------------------------------------------- */
+#ifndef MJPEG423_B200_NO_REFERENCE_TYPES
+/* mjpeg423_types.h:15-19: `bool` is `int` in the reference ABI; spelled int below. */
+typedef struct { uint32_t frame_index; uint32_t frame_position; } iframe_trailer_t; /* :22-25 */
+typedef uint8_t color_block_t[8][8];    /* :33 */
+typedef uint8_t (*pcolor_block_t)[8];   /* :34 */
+#ifndef DCTELEM
+#define DCTELEM int16_t                 /* :39 */
+#endif
+typedef DCTELEM dct_block_t[8][8];      /* :42 */
+typedef DCTELEM (*pdct_block_t)[8];     /* :43 */
+typedef struct { uint8_t blue, green, red, alpha; } rgb_pixel_t; /* :56-61, BMP byte order */
+#endif
+
+/* ---- 1. reference library seam: LIB/decoder/mjpeg423_decoder.h:14-17 ------------------------------ */
+/* P is the reference's `bool` (int).  DCACq is in/out: for P != 0 decoded deltas are ADDED to it
+ * (LIB/decoder/lossless_decode.c:90-92,121-123).  The bitstream must be readable 4 bytes past its last
+ * symbol; because the reference signature carries no length, the shim reads at most
+ * mjpeg423_b200_get_read_limit() bytes (default: num_blocks*152 + 8, the longest conforming stream). */
+void lossless_decode(int num_blocks, void* bitstream, dct_block_t* DCACq, dct_block_t quant, int P);
+void idct(dct_block_t DCAC, color_block_t block);
+void ycbcr_to_rgb(int h, int w, uint32_t w_size, pcolor_block_t Y, pcolor_block_t Cb, pcolor_block_t Cr,
+                  rgb_pixel_t* rgbblock);
+/* Decodes file `filename_in` and writes one 32-bpp BMP per frame, names derived from
+ * `filenamebase_out` ("name0000.bmp" pattern, LIB/decoder/mjpeg423_decoder.c:127-132). */
+void mjpeg423_decode(const char* filename_in, const char* filenamebase_out);
+extern dct_block_t Yquant;              /* LIB/common/tables.c:13-21 */
+extern dct_block_t Cquant;              /* LIB/common/tables.c:24-32 */
+extern int zigzag_table[64];            /* LIB/common/tables.c:35-42 */
+
+void   mjpeg423_b200_set_read_limit(size_t bytes);   /* 0 restores the default */
+size_t mjpeg423_b200_get_read_limit(void);
+
+/* Plane-at-a-time variants of the per-block shims (same arithmetic, one launch per call):
+ * n blocks of coefficients -> n blocks of samples; block-major planes -> W x H BGRA raster. */
+int mjpeg423_b200_idct_blocks(const int16_t* coef, uint8_t* samples, size_t n_blocks);
+int mjpeg423_b200_ycbcr_to_rgb_frame(const uint8_t* Y, const uint8_t* Cb, const uint8_t* Cr, uint32_t w_size,
+                                     uint32_t h_size, rgb_pixel_t* rgb);
+/* lossless_decode with an explicit stream length. */
+int mjpeg423_b200_lossless_decode(int num_blocks, const void* bitstream, size_t bitstream_len,
+                                  int16_t* DCACq, const int16_t* quant, int P);
+
+/* ---- 2. reference accelerator seam: C0/idct_ycbcr_to_rgb_accel.h:13-22 ----------------------------- */
+/* Asynchronous: the calculate_buffer_* calls enqueue the upload of one dequantised coefficient plane
+ * (sizeOfInputBuffer bytes = blocks*128, C0/playback.c:71-75,102-103); get_results enqueues IDCT +
+ * colour conversion of the three planes and the read-back of the BGRA frame into outputBuffer
+ * (C0/playback.c:108-109); the wait_* calls block like the reference's CSR busy-polls
+ * (C0/idct_ycbcr_to_rgb_accel.c:84-98).  Frame geometry defaults to the reference's 640x480
+ * (COMMON/config.h:23-24) and is changed with mjpeg423_b200_accel_set_geometry. */
+int  init_idct_ycbcr_to_rgb_accel(void);
+void idct_accel_calculate_buffer_y(void* inputBuffer, uint32_t sizeOfInputBuffer);
+void idct_accel_calculate_buffer_cb(void* inputBuffer, uint32_t sizeOfInputBuffer);
+void idct_accel_calculate_buffer_cr(void* inputBuffer, uint32_t sizeOfInputBuffer);
+void ycbcr_to_rgb_accel_get_results(void* outputBuffer, uint32_t sizeOfOutputBuffer);
+void wait_for_ycbcr_to_rgb_finsh(void);   /* sic: reference spelling */
+void wait_for_idct_y_finsh(void);
+int  mjpeg423_b200_accel_set_geometry(uint32_t w_size, uint32_t h_size);
+
+/* ---- 3. throughput API ------------------------------------------------------------------------------ */
+#define MJPEG423_OK            0
+#define MJPEG423_E_ARG        -1   /* bad argument / geometry (W, H must be non-zero multiples of 8) */
+#define MJPEG423_E_FORMAT     -2   /* container does not parse (truncated, sizes inconsistent) */
+#define MJPEG423_E_CUDA       -3   /* CUDA runtime error or no device (see mjpeg423_b200_last_error) */
+#define MJPEG423_E_NOMEM      -4
+#define MJPEG423_E_STREAM     -5   /* a plane stream did not contain num_blocks blocks */
+#define MJPEG423_E_PFRAME     -6   /* frame range starts on a P frame (needs the preceding I frame) */
+
+typedef struct mjpeg423_b200_ctx mjpeg423_b200_ctx;
+
+typedef struct {
+    uint32_t num_frames, w_size, h_size, num_iframes, payload_size; /* file header, mjpeg423_decoder.c:33-38 */
+    uint32_t num_pframes;
+    uint64_t frame_bytes;        /* w_size*h_size*4: one decoded BGRA frame */
+    uint64_t max_frame_payload;  /* largest frame record */
+} mjpeg423_b200_info;
+
+typedef struct {
+    /* CUDA-event times (ms) of the most recent decode on this context, measured on the library's
+     * compute stream.  Stage times are only collected when profiling is on (set_option PROFILE 1),
+     * because the extra events serialise the stages. */
+    float total_ms;              /* whole device-side decode (all kernels of the call) */
+    float entropy_sync_ms;       /* speculative parse + merge + chain kernels */
+    float entropy_write_ms;      /* coefficient write kernel */
+    float idct_colour_ms;        /* fused IDCT + colour kernel (or idct_ms + colour_ms when staged) */
+    float idct_ms, colour_ms;
+    uint64_t kernel_launches;    /* kernels launched by the call */
+    uint64_t payload_bytes;      /* compressed bytes consumed (sum of plane streams) */
+    uint64_t segments, fixups;   /* bitstream segments / segments re-parsed by the chain kernel */
+    uint64_t frames;
+} mjpeg423_b200_stats;
+
+enum {
+    MJPEG423_OPT_PROFILE      = 1,  /* 0/1: collect per-stage event times */
+    MJPEG423_OPT_STAGED       = 2,  /* 0: fused IDCT+colour kernel (default); 1: separate idct and colour kernels */
+    MJPEG423_OPT_CHUNK_FRAMES = 3,  /* frames per pipeline chunk in the host-buffer path (0 = auto) */
+    MJPEG423_OPT_VALIDATE     = 4   /* 0/1: check every stream decoded exactly num_blocks blocks (default 1) */
+};
+
+int  mjpeg423_b200_create(mjpeg423_b200_ctx** ctx, int device);
+void mjpeg423_b200_destroy(mjpeg423_b200_ctx* ctx);
+int  mjpeg423_b200_set_option(mjpeg423_b200_ctx* ctx, int option, int64_t value);
+const char* mjpeg423_b200_last_error(void);      /* thread-local, never NULL */
+
+/* Parse the header of an in-memory .mpg (layout: SURVEY.md A.1). */
+int mjpeg423_b200_probe(const uint8_t* mpg, size_t len, mjpeg423_b200_info* info);
+
+/* Custom quantisation tables (natural order, 64 x int16 each); NULL restores Yquant / Cquant.  The file
+ * format carries no tables: like the reference, they are a parameter of the decode
+ * (LIB/decoder/mjpeg423_decoder.c:110-112). */
+int mjpeg423_b200_set_quant(mjpeg423_b200_ctx* ctx, const int16_t* yquant, const int16_t* cquant);
+
+/* End-to-end: decode frames [first, first+n) of the .mpg held in HOST memory into `out`.
+ * out_on_device == 0: out is host memory (n * frame_bytes); pinned memory (mjpeg423_b200_host_alloc)
+ * gives full PCIe speed.  The call uploads the bitstream, decodes and reads back in overlapping
+ * chunks on several CUDA streams and returns when `out` is complete.
+ * out_on_device != 0: out is device memory on the context's device; no read-back. */
+int mjpeg423_b200_decode_frames(mjpeg423_b200_ctx* ctx, const uint8_t* mpg, size_t len, uint32_t first,
+                                uint32_t n, void* out, int out_on_device);
+
+/* Device-resident variant: upload once, decode many times (bench `value`, long-lived servers).
+ * upload() parses frames [first, first+n), copies their payload to HBM and builds the stream tables;
+ * decode_resident() runs only kernels and writes n * frame_bytes to device memory d_out. */
+int mjpeg423_b200_upload(mjpeg423_b200_ctx* ctx, const uint8_t* mpg, size_t len, uint32_t first, uint32_t n);
+int mjpeg423_b200_decode_resident(mjpeg423_b200_ctx* ctx, void* d_out);
+int mjpeg423_b200_get_stats(mjpeg423_b200_ctx* ctx, mjpeg423_b200_stats* stats);
+
+/* Stage-level device entry points on the resident job (per-stage profiling and parity tests):
+ * coefficient planes are n frames x 3 planes x nb blocks x 64 int16 (frame-major, Y|Cb|Cr);
+ * sample planes the same shape in uint8. */
+int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* ctx, int16_t* d_coef);
+int mjpeg423_b200_resident_idct(mjpeg423_b200_ctx* ctx, const int16_t* d_coef, uint8_t* d_samples);
+int mjpeg423_b200_resident_colour(mjpeg423_b200_ctx* ctx, const uint8_t* d_samples, void* d_out);
+int mjpeg423_b200_resident_idct_colour(mjpeg423_b200_ctx* ctx, const int16_t* d_coef, void* d_out);
+
+/* Memory helpers (so a C caller needs no CUDA headers). */
+void* mjpeg423_b200_host_alloc(size_t bytes);     /* pinned host memory, NULL on failure */
+void  mjpeg423_b200_host_free(void* p);
+void* mjpeg423_b200_device_alloc(mjpeg423_b200_ctx* ctx, size_t bytes);
+void  mjpeg423_b200_device_free(mjpeg423_b200_ctx* ctx, void* p);
+int   mjpeg423_b200_memcpy_d2h(mjpeg423_b200_ctx* ctx, void* dst, const void* d_src, size_t bytes);
+int   mjpeg423_b200_memcpy_h2d(mjpeg423_b200_ctx* ctx, void* d_dst, const void* src, size_t bytes);
+int   mjpeg423_b200_sync(mjpeg423_b200_ctx* ctx);
+int   mjpeg423_b200_device_count(void);
+/* 64-bit FNV-1a hash of every frame of a device-resident output (n x frame_bytes), computed on the GPU;
+ * hashes (n x uint64) is host memory.  Used by the bench for whole-batch bit-exactness checks. */
+int   mjpeg423_b200_hash_frames(mjpeg423_b200_ctx* ctx, const void* d_frames, uint64_t frame_bytes, uint32_t n,
+                                uint64_t* hashes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MJPEG423_B200_H */

@@ -1,0 +1,212 @@
+// common.cuh -- shared device helpers for the MJPEG423 kernels (sm_100a).
+//
+// LIB = /root/reference/core0/software/common/libs/mjpeg423.  Every arithmetic helper here restates
+// one reference macro or statement and cites it; results must be bit-identical to the C reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mj {
+
+// ------------------------------------------------------------------------------------------------
+// Layout constants of the entropy stage.
+// A plane bitstream is cut into fixed SEG_BYTES segments; a segment owns the blocks whose FIRST bit
+// lies inside it.  CP_BITS is the spacing of the merge checkpoints inside a segment.
+// ------------------------------------------------------------------------------------------------
+constexpr int SEG_BYTES = 256;
+constexpr int SEG_BITS = SEG_BYTES * 8;
+constexpr int CP_BITS = 256;
+constexpr int NCP = SEG_BITS / CP_BITS;        // checkpoints per segment (the last one is the segment end)
+constexpr int ENT_TPB = 128;                   // threads per CTA in the entropy kernels
+constexpr int MIN_BLOCK_BITS = 12;             // DC size 0 + END
+constexpr uint32_t RUNAWAY_BITS = 8192;        // parse guard for non-conforming / speculative garbage
+constexpr uint32_t MAX_STREAM_BYTES = 1u << 28; // bit positions are 32-bit
+
+// One plane bitstream of one frame (built by the host from the 16-byte frame headers,
+// LIB/decoder/mjpeg423_decoder.c:94-107).
+struct StreamDesc {
+    uint64_t byte_off;     // offset of the stream's first byte in the device payload buffer
+    uint32_t byte_len;     // Ysize / Cbsize / implied Crsize
+    uint32_t nb;           // blocks per plane
+    uint32_t seg_base;     // index of this stream's first segment in the per-segment arrays
+    uint32_t nseg;         // ceil(byte_len / SEG_BYTES), at least 1
+    uint32_t block_base;   // index (in 64-coefficient blocks) of this plane in the coefficient buffer
+    uint16_t quant_id;     // 0 = luminance table, 1 = chrominance table
+    uint16_t ptype;        // 0 = I frame (zero-fill, DC differential), 1 = P frame (accumulate)
+};
+
+// A CTA-sized run of consecutive segments of one stream.
+struct TileDesc {
+    uint32_t stream;       // index into the StreamDesc array
+    uint32_t seg0;         // first segment (within the stream) owned by this tile
+};
+
+// ------------------------------------------------------------------------------------------------
+// MSB-first bit reader over global memory: 64-bit window, refilled by aligned 32-bit words.
+// Replaces update_buffer / INPUT_BITS (LIB/decoder/lossless_decode.c:139-162,207); only the number
+// of consumed bits is observable, so the window width is free.  The payload buffer is padded so
+// that reads up to 16 bytes past any stream end are in bounds.
+// ------------------------------------------------------------------------------------------------
+struct BitReader {
+    const uint32_t* wp;    // next aligned word
+    uint64_t buf;          // next bit is bit 63
+    int nbits;             // valid bits in buf
+
+    __device__ __forceinline__ void init(const uint8_t* base, uint32_t bitpos) {
+        uintptr_t a = reinterpret_cast<uintptr_t>(base) + (bitpos >> 3);
+        uint32_t skip = (uint32_t)(a & 3u) * 8u + (bitpos & 7u);
+        wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        uint32_t w0 = __byte_perm(__ldg(wp), 0, 0x0123);
+        uint32_t w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);
+        wp += 2;
+        buf = (((uint64_t)w0 << 32) | w1) << skip;
+        nbits = 64 - (int)skip;
+    }
+    // Guarantees >= 32 valid bits (the longest symbol is 8 + 15 = 23 bits).
+    __device__ __forceinline__ void refill() {
+        if (nbits <= 32) {
+            uint32_t w = __byte_perm(__ldg(wp), 0, 0x0123);
+            wp++;
+            buf |= (uint64_t)w << (32 - nbits);
+            nbits += 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t top() const { return (uint32_t)(buf >> 32); }
+    __device__ __forceinline__ void skip(int n) { buf <<= n; nbits -= n; }
+};
+
+// JPEG VLI sign extension: HUFF_EXTEND, LIB/decoder/lossless_decode.c:204.  size in 1..15.
+__device__ __forceinline__ int vli_extend(uint32_t amp, int size) {
+    return (amp < (1u << (size - 1))) ? (int)amp - (1 << size) + 1 : (int)amp;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block parser shared by every entropy kernel so that the speculative, merge and write passes follow
+// the SAME trajectory function.  Parses one block starting at r (positioned on a DC symbol) and
+// returns the number of bits consumed.  Sink::dc(e) / Sink::ac(zigzag_index, e) receive the symbols.
+//   DC symbol  input_DC  LIB/decoder/lossless_decode.c:210-224  (4-bit size + amplitude)
+//   AC symbol  input_AC  :227-246 (4-bit run, 4-bit size, amplitude); size 0: run 15 = ZRL else END
+//   block loop :101-133; `index` is uint8_t there and wraps, so it does here.
+// max_bits bounds the parse on non-conforming input (memory safety; conforming blocks are <= 1212 bits).
+// ------------------------------------------------------------------------------------------------
+template <class Sink>
+__device__ __forceinline__ uint32_t parse_block(BitReader& r, uint32_t max_bits, Sink& sink) {
+    r.refill();
+    uint32_t t = r.top();
+    int size = (int)(t >> 28);
+    int e = 0;
+    if (size) e = vli_extend((t << 4) >> (32 - size), size);
+    r.skip(4 + size);
+    uint32_t used = 4u + (uint32_t)size;
+    sink.dc(e);
+    uint32_t idx = 1;
+    while (used < max_bits) {
+        r.refill();
+        t = r.top();
+        int run = (int)(t >> 28);
+        size = (int)((t >> 24) & 15u);
+        r.skip(8 + size);
+        used += 8u + (uint32_t)size;
+        if (size == 0) {
+            if (run != 15) break;             // END
+            idx = (idx + 16u) & 255u;         // ZRL
+            continue;
+        }
+        e = vli_extend((t << 8) >> (32 - size), size);
+        idx = (idx + (uint32_t)run) & 255u;
+        if (idx < 64u) sink.ac(idx, e);
+        if (idx >= 63u) break;
+        idx++;
+    }
+    return used;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 8-point LL&M inverse DCT pass: LIB/decoder/idct.c:46-97 (pass 1) == :123-168 (pass 2).
+// Constants LIB/common/dct_math.h:53-64.  All arithmetic is int32 with wrap-around, exactly the
+// reference's operation order (MULTIPLY is a plain 32-bit multiply, dct_math.h:76).
+// SHIFT = 11 for pass 1 (CONST_BITS - PASS1_BITS), 18 for pass 2 (CONST_BITS + PASS1_BITS + 3).
+// ------------------------------------------------------------------------------------------------
+template <int SHIFT>
+__device__ __forceinline__ void idct8(int i0, int i1, int i2, int i3, int i4, int i5, int i6, int i7,
+                                      int (&o)[8]) {
+    constexpr int RND = 1 << (SHIFT - 1);   // DESCALE, dct_math.h:48
+    int z1 = (i2 + i6) * 4433;
+    int tmp2 = z1 + i6 * -15137;
+    int tmp3 = z1 + i2 * 6270;
+    int tmp0 = (int)((unsigned)(i0 + i4) << 13);
+    int tmp1 = (int)((unsigned)(i0 - i4) << 13);
+    int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    int a0 = i7, a1 = i5, a2 = i3, a3 = i1;
+    int y1 = a0 + a3, y2 = a1 + a2, y3 = a0 + a2, y4 = a1 + a3;
+    int y5 = (y3 + y4) * 9633;
+    a0 *= 2446; a1 *= 16819; a2 *= 25172; a3 *= 12299;
+    y1 *= -7373; y2 *= -20995;
+    y3 = y3 * -16069 + y5;
+    y4 = y4 * -3196 + y5;
+    a0 += y1 + y3; a1 += y2 + y4; a2 += y2 + y3; a3 += y1 + y4;
+    o[0] = (tmp10 + a3 + RND) >> SHIFT;
+    o[7] = (tmp10 - a3 + RND) >> SHIFT;
+    o[1] = (tmp11 + a2 + RND) >> SHIFT;
+    o[6] = (tmp11 - a2 + RND) >> SHIFT;
+    o[2] = (tmp12 + a1 + RND) >> SHIFT;
+    o[5] = (tmp12 - a1 + RND) >> SHIFT;
+    o[3] = (tmp13 + a0 + RND) >> SHIFT;
+    o[4] = (tmp13 - a0 + RND) >> SHIFT;
+}
+
+__device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xFFFFu); }
+__device__ __forceinline__ int hi16(uint32_t w) { return (int)w >> 16; }
+__device__ __forceinline__ uint32_t clamp255(int v) { return (uint32_t)min(max(v, 0), 255); }  // NORMALIZE, idct.c:20
+
+// Full 8x8 IDCT of one block held as 8 rows of packed int16 (uint4 = one 16-byte row).
+// Output: 16 words, word 2r / 2r+1 = pixels 0-3 / 4-7 of row r (little-endian bytes).
+__device__ __forceinline__ void idct_block(const uint4 (&rows)[8], uint32_t (&out)[16]) {
+    int ws[8][8];
+    // Pass 1: columns (idct.c:41-109).  Column c takes element c of every row.
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int in[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            uint32_t w = (c >> 1) == 0 ? rows[r].x : (c >> 1) == 1 ? rows[r].y : (c >> 1) == 2 ? rows[r].z : rows[r].w;
+            in[r] = (c & 1) ? hi16(w) : lo16(w);
+        }
+        int o[8];
+        idct8<11>(in[0], in[1], in[2], in[3], in[4], in[5], in[6], in[7], o);
+#pragma unroll
+        for (int r = 0; r < 8; r++) ws[r][c] = o[r];
+    }
+    // Pass 2: rows (idct.c:116-180), clamp to 0..255, no level shift.
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        int o[8];
+        idct8<18>(ws[r][0], ws[r][1], ws[r][2], ws[r][3], ws[r][4], ws[r][5], ws[r][6], ws[r][7], o);
+        out[2 * r] = clamp255(o[0]) | (clamp255(o[1]) << 8) | (clamp255(o[2]) << 16) | (clamp255(o[3]) << 24);
+        out[2 * r + 1] = clamp255(o[4]) | (clamp255(o[5]) << 8) | (clamp255(o[6]) << 16) | (clamp255(o[7]) << 24);
+    }
+}
+
+// YCbCr -> packed BGRA word: LIB/decoder/ycbcr_to_rgb.c:31-46.  NORMALIZE_RGB (:19): negative -> 0,
+// else >> 14 then cap at 255.  Word = B | G<<8 | R<<16 | A(0)<<24 (rgb_pixel_t, mjpeg423_types.h:56-61).
+__device__ __forceinline__ uint32_t ycc_to_bgra(uint32_t y, uint32_t cb, uint32_t cr) {
+    int cbb = (int)cb - 128, crr = (int)cr - 128;
+    int yy = (int)(y << 14);
+    int r = yy + 22970 * crr;
+    int g = yy - 5638 * cbb - 11700 * crr;
+    int b = yy + 29032 * cbb;
+    // max(t,0) >> 14 then min(.,255) == NORMALIZE_RGB
+    uint32_t R = (uint32_t)min(max(r, 0) >> 14, 255);
+    uint32_t G = (uint32_t)min(max(g, 0) >> 14, 255);
+    uint32_t B = (uint32_t)min(max(b, 0) >> 14, 255);
+    return B | (G << 8) | (R << 16);
+}
+
+// 256-bit global store (sm_100+): one full 32-byte sector per lane.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+}  // namespace mj

@@ -1,0 +1,624 @@
+// runtime.cu -- host runtime: container walk, stream/tile tables, device buffers and the chunked
+// multi-stream decode pipeline behind the throughput API of include/mjpeg423_b200.h.
+//
+// It batches the per-frame loop body of the reference decoder,
+// LIB/decoder/mjpeg423_decoder.c:90-124 (LIB = /root/reference/core0/software/common/libs/mjpeg423):
+// read frame header -> 3 x lossless_decode -> 3*nb x idct -> nb x ycbcr_to_rgb, over a frame range.
+#include "runtime.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace mj {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+const std::string& last_error() { return g_last_error; }
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return MJPEG423_E_CUDA;
+}
+#define CU(call)                                                \
+    do {                                                        \
+        cudaError_t e_ = (call);                                \
+        if (e_ != cudaSuccess) return mj::cuda_fail(e_, #call); \
+    } while (0)
+
+static inline uint32_t rd32(const uint8_t* p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// File header: 5 x u32 {num_frames, w_size, h_size, num_iframes, payload_size}; then per frame a 16-byte
+// header {frame_size (incl. header, padded to x4), frame_type, Ysize, Cbsize} + Y|Cb|Cr streams.
+int parse_mpg(const uint8_t* mpg, size_t len, MpgIndex& idx, bool headers_only) {
+    if (!mpg || len < 20) { set_error("mpg: shorter than the 20-byte file header"); return MJPEG423_E_FORMAT; }
+    mjpeg423_b200_info& in = idx.info;
+    in.num_frames = rd32(mpg); in.w_size = rd32(mpg + 4); in.h_size = rd32(mpg + 8);
+    in.num_iframes = rd32(mpg + 12); in.payload_size = rd32(mpg + 16);
+    if (!in.w_size || !in.h_size || (in.w_size & 7) || (in.h_size & 7)) {
+        set_error("mpg: width and height must be non-zero multiples of 8");   // mjpeg423_decoder.c:45-48: no edge handling
+        return MJPEG423_E_ARG;
+    }
+    in.frame_bytes = (uint64_t)in.w_size * in.h_size * 4;
+    in.num_pframes = 0; in.max_frame_payload = 0;
+    idx.frames.clear();
+    if (headers_only && in.num_frames == 0) return MJPEG423_OK;
+    idx.frames.reserve(in.num_frames);
+    uint64_t off = 20;
+    for (uint32_t f = 0; f < in.num_frames; f++) {
+        if (off + 16 > len) { set_error("mpg: truncated at frame header " + std::to_string(f)); return MJPEG423_E_FORMAT; }
+        FrameRec r;
+        r.off = off; r.size = rd32(mpg + off); r.type = rd32(mpg + off + 4);
+        r.ysize = rd32(mpg + off + 8); r.cbsize = rd32(mpg + off + 12);
+        if (r.size < 16 || off + r.size > len || (uint64_t)r.ysize + r.cbsize > r.size - 16u || r.type > 1) {
+            set_error("mpg: inconsistent sizes in frame " + std::to_string(f));
+            return MJPEG423_E_FORMAT;
+        }
+        r.crsize = r.size - 16u - r.ysize - r.cbsize;     // implied; includes the 0-3 pad bytes
+        if (r.type) in.num_pframes++;
+        in.max_frame_payload = std::max<uint64_t>(in.max_frame_payload, r.size);
+        idx.frames.push_back(r);
+        off += r.size;
+    }
+    return MJPEG423_OK;
+}
+
+int build_plan(const MpgIndex& idx, uint32_t first, uint32_t n, Plan& plan) {
+    const mjpeg423_b200_info& in = idx.info;
+    if ((uint64_t)first + n > idx.frames.size()) { set_error("frame range exceeds num_frames"); return MJPEG423_E_ARG; }
+    plan = Plan();
+    plan.W = in.w_size; plan.H = in.h_size; plan.nb = (in.w_size / 8) * (in.h_size / 8);
+    plan.first = first; plan.n = n;
+    if (n == 0) return MJPEG423_OK;
+    if (idx.frames[first].type != 0) {
+        set_error("frame range starts on a P frame; start at an I frame (use the trailer / probe)");
+        return MJPEG423_E_PFRAME;
+    }
+    if ((uint64_t)n * 3 * plan.nb >= 0xFFFFFFFFull) { set_error("too many blocks in one plan"); return MJPEG423_E_ARG; }
+    plan.frames.assign(idx.frames.begin() + first, idx.frames.begin() + first + n);
+    plan.payload_off = plan.frames.front().off;
+    plan.payload_len = plan.frames.back().off + plan.frames.back().size - plan.payload_off;
+    plan.streams.reserve((size_t)n * 3);
+    plan.f_sync0.resize(n + 1); plan.f_write0.resize(n + 1); plan.f_seg0.resize(n + 1);
+    uint32_t seg_base = 0;
+    for (uint32_t f = 0; f < n; f++) {
+        const FrameRec& r = plan.frames[f];
+        plan.f_sync0[f] = (uint32_t)plan.sync_tiles.size();
+        plan.f_write0[f] = (uint32_t)plan.write_tiles.size();
+        plan.f_seg0[f] = seg_base;
+        const uint32_t lens[3] = {r.ysize, r.cbsize, r.crsize};
+        uint64_t so = r.off + 16 - plan.payload_off;
+        for (int p = 0; p < 3; p++) {
+            if (lens[p] >= MAX_STREAM_BYTES) { set_error("plane stream too large"); return MJPEG423_E_ARG; }
+            StreamDesc sd;
+            sd.byte_off = so; sd.byte_len = lens[p]; sd.nb = plan.nb;
+            sd.seg_base = seg_base;
+            sd.nseg = std::max<uint32_t>(1, (lens[p] + SEG_BYTES - 1) / SEG_BYTES);
+            sd.block_base = (f * 3 + p) * plan.nb;
+            sd.quant_id = p ? 1 : 0; sd.ptype = (uint16_t)r.type;
+            const uint32_t sidx = (uint32_t)plan.streams.size();
+            for (uint32_t s0 = 0; s0 < sd.nseg; s0 += ENT_TPB - 1) plan.sync_tiles.push_back({sidx, s0});
+            for (uint32_t s0 = 0; s0 < sd.nseg; s0 += ENT_TPB) plan.write_tiles.push_back({sidx, s0});
+            plan.streams.push_back(sd);
+            seg_base += sd.nseg; so += lens[p];
+            plan.stream_bytes += lens[p];
+        }
+    }
+    plan.f_sync0[n] = (uint32_t)plan.sync_tiles.size();
+    plan.f_write0[n] = (uint32_t)plan.write_tiles.size();
+    plan.f_seg0[n] = seg_base;
+    return MJPEG423_OK;
+}
+
+}  // namespace mj
+
+using namespace mj;
+
+int DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return MJPEG423_OK;
+    release();
+    size_t want = (bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; cap = 0; cuda_fail(e, "cudaMalloc"); return MJPEG423_E_NOMEM; }
+    cap = want;
+    return MJPEG423_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+}
+
+// ---- default tables: LIB/common/tables.c:13-32 -------------------------------------------------------
+extern "C" {
+dct_block_t Yquant = {{16, 11, 10, 16, 24, 40, 51, 61},     {12, 12, 14, 19, 26, 58, 60, 55},
+                      {14, 13, 16, 24, 40, 57, 69, 56},     {14, 17, 22, 29, 51, 87, 80, 62},
+                      {18, 22, 37, 56, 68, 109, 103, 77},   {24, 35, 55, 64, 81, 104, 113, 92},
+                      {49, 64, 78, 87, 103, 121, 120, 101}, {72, 92, 95, 98, 112, 100, 103, 99}};
+dct_block_t Cquant = {{17, 18, 24, 47, 99, 99, 99, 99}, {18, 21, 26, 66, 99, 99, 99, 99},
+                      {24, 26, 56, 99, 99, 99, 99, 99}, {47, 66, 99, 99, 99, 99, 99, 99},
+                      {99, 99, 99, 99, 99, 99, 99, 99}, {99, 99, 99, 99, 99, 99, 99, 99},
+                      {99, 99, 99, 99, 99, 99, 99, 99}, {99, 99, 99, 99, 99, 99, 99, 99}};
+int zigzag_table[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                        41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                        30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+}
+
+// ---- context ----------------------------------------------------------------------------------------
+extern "C" int mjpeg423_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char* mjpeg423_b200_last_error(void) { return mj::last_error().c_str(); }
+
+extern "C" int mjpeg423_b200_create(mjpeg423_b200_ctx** out, int device) {
+    if (!out) return MJPEG423_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error(std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                  " (this library has no CPU fallback)");
+        cudaGetLastError();
+        return MJPEG423_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("bad device ordinal"); return MJPEG423_E_ARG; }
+    CU(cudaSetDevice(device));
+    mjpeg423_b200_ctx* c = new mjpeg423_b200_ctx();
+    c->device = device;
+    CU(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+    for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
+    CU(cudaMalloc(&c->d_quant, sizeof(c->h_quant)));
+    *out = c;
+    return mjpeg423_b200_set_quant(c, nullptr, nullptr);
+}
+
+extern "C" void mjpeg423_b200_destroy(mjpeg423_b200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&c->payload, &c->tables, &c->segs, &c->coef[0], &c->coef[1], &c->samples, &c->stream_blocks,
+                      &c->misc, &c->in_ring[0], &c->in_ring[1], &c->out_ring[0], &c->out_ring[1]})
+        b->release();
+    for (int i = 0; i < 2; i++) if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+    if (c->d_quant) cudaFree(c->d_quant);
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t s : {c->s_compute, c->s_in, c->s_out, c->s_aux}) if (s) cudaStreamDestroy(s);
+    delete c;
+}
+
+extern "C" int mjpeg423_b200_set_option(mjpeg423_b200_ctx* c, int option, int64_t value) {
+    if (!c) return MJPEG423_E_ARG;
+    switch (option) {
+        case MJPEG423_OPT_PROFILE: c->profile = value != 0; return MJPEG423_OK;
+        case MJPEG423_OPT_STAGED: c->staged = value != 0; return MJPEG423_OK;
+        case MJPEG423_OPT_CHUNK_FRAMES: c->chunk_frames = value < 0 ? 0 : (uint32_t)value; return MJPEG423_OK;
+        case MJPEG423_OPT_VALIDATE: c->validate = value != 0; return MJPEG423_OK;
+    }
+    set_error("unknown option");
+    return MJPEG423_E_ARG;
+}
+
+extern "C" int mjpeg423_b200_set_quant(mjpeg423_b200_ctx* c, const int16_t* yq, const int16_t* cq) {
+    if (!c) return MJPEG423_E_ARG;
+    CU(cudaSetDevice(c->device));
+    std::memcpy(c->h_quant, yq ? yq : &Yquant[0][0], 128);
+    std::memcpy(c->h_quant + 64, cq ? cq : &Cquant[0][0], 128);
+    CU(cudaMemcpyAsync(c->d_quant, c->h_quant, sizeof(c->h_quant), cudaMemcpyHostToDevice, c->s_compute));
+    CU(cudaStreamSynchronize(c->s_compute));
+    return MJPEG423_OK;
+}
+
+extern "C" int mjpeg423_b200_probe(const uint8_t* mpg, size_t len, mjpeg423_b200_info* info) {
+    if (!info) return MJPEG423_E_ARG;
+    MpgIndex idx;
+    int rc = parse_mpg(mpg, len, idx, false);
+    *info = idx.info;
+    return rc;
+}
+
+// ---- plan upload --------------------------------------------------------------------------------------
+namespace {
+
+struct Tables {           // device addresses inside ctx->tables / ctx->segs
+    StreamDesc* streams; TileDesc* sync_tiles; TileDesc* write_tiles;
+    uint32_t *seg_entry, *seg_exit, *seg_cd, *seg_first, *stream_blocks;
+    unsigned long long* fixups;
+};
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Lays the plan's tables out in ctx->tables (uploaded) and ctx->segs (device scratch).
+int upload_tables(mjpeg423_b200_ctx* c, const Plan& plan, Tables& t, cudaStream_t s) {
+    const size_t b_streams = align256(plan.streams.size() * sizeof(StreamDesc));
+    const size_t b_sync = align256(plan.sync_tiles.size() * sizeof(TileDesc));
+    const size_t b_write = align256(plan.write_tiles.size() * sizeof(TileDesc));
+    int rc = c->tables.reserve(b_streams + b_sync + b_write + 256);
+    if (rc) return rc;
+    uint8_t* base = c->tables.as<uint8_t>();
+    t.streams = reinterpret_cast<StreamDesc*>(base);
+    t.sync_tiles = reinterpret_cast<TileDesc*>(base + b_streams);
+    t.write_tiles = reinterpret_cast<TileDesc*>(base + b_streams + b_sync);
+    CU(cudaMemcpyAsync(t.streams, plan.streams.data(), plan.streams.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(t.sync_tiles, plan.sync_tiles.data(), plan.sync_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(t.write_tiles, plan.write_tiles.data(), plan.write_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
+    const size_t nseg = plan.f_seg0.empty() ? 0 : plan.f_seg0.back();
+    const size_t b_seg = align256(nseg * 4);
+    const size_t b_sb = align256(plan.streams.size() * 4);
+    rc = c->segs.reserve(4 * b_seg + b_sb + 256);
+    if (rc) return rc;
+    uint8_t* sb = c->segs.as<uint8_t>();
+    t.seg_entry = reinterpret_cast<uint32_t*>(sb);
+    t.seg_exit = reinterpret_cast<uint32_t*>(sb + b_seg);
+    t.seg_cd = reinterpret_cast<uint32_t*>(sb + 2 * b_seg);
+    t.seg_first = reinterpret_cast<uint32_t*>(sb + 3 * b_seg);
+    t.stream_blocks = reinterpret_cast<uint32_t*>(sb + 4 * b_seg);
+    t.fixups = reinterpret_cast<unsigned long long*>(sb + 4 * b_seg + b_sb);
+    return MJPEG423_OK;
+}
+
+Tables tables_of(mjpeg423_b200_ctx* c, const Plan& plan) {   // recompute the layout of upload_tables
+    Tables t;
+    const size_t b_streams = align256(plan.streams.size() * sizeof(StreamDesc));
+    const size_t b_sync = align256(plan.sync_tiles.size() * sizeof(TileDesc));
+    uint8_t* base = c->tables.as<uint8_t>();
+    t.streams = reinterpret_cast<StreamDesc*>(base);
+    t.sync_tiles = reinterpret_cast<TileDesc*>(base + b_streams);
+    t.write_tiles = reinterpret_cast<TileDesc*>(base + b_streams + b_sync);
+    const size_t nseg = plan.f_seg0.empty() ? 0 : plan.f_seg0.back();
+    const size_t b_seg = align256(nseg * 4), b_sb = align256(plan.streams.size() * 4);
+    uint8_t* sb = c->segs.as<uint8_t>();
+    t.seg_entry = reinterpret_cast<uint32_t*>(sb);
+    t.seg_exit = reinterpret_cast<uint32_t*>(sb + b_seg);
+    t.seg_cd = reinterpret_cast<uint32_t*>(sb + 2 * b_seg);
+    t.seg_first = reinterpret_cast<uint32_t*>(sb + 3 * b_seg);
+    t.stream_blocks = reinterpret_cast<uint32_t*>(sb + 4 * b_seg);
+    t.fixups = reinterpret_cast<unsigned long long*>(sb + 4 * b_seg + b_sb);
+    return t;
+}
+
+uint32_t auto_chunk(const Plan& plan, uint64_t target_bytes, uint64_t bytes_per_frame) {
+    uint64_t k = target_bytes / std::max<uint64_t>(1, bytes_per_frame);
+    k = std::max<uint64_t>(1, std::min<uint64_t>(k, plan.n));
+    return (uint32_t)k;
+}
+
+EntropyJob make_job(const Plan& plan, const Tables& t, const uint8_t* d_payload_origin, uint32_t f0, uint32_t f1) {
+    EntropyJob j;
+    j.d_payload = d_payload_origin;
+    j.d_streams = t.streams;
+    j.d_sync_tiles = t.sync_tiles + plan.f_sync0[f0];
+    j.d_write_tiles = t.write_tiles + plan.f_write0[f0];
+    j.stream_lo = f0 * 3; j.n_streams = (f1 - f0) * 3;
+    j.n_sync_tiles = plan.f_sync0[f1] - plan.f_sync0[f0];
+    j.n_write_tiles = plan.f_write0[f1] - plan.f_write0[f0];
+    j.d_seg_entry = t.seg_entry; j.d_seg_exit = t.seg_exit; j.d_seg_cd = t.seg_cd; j.d_seg_first = t.seg_first;
+    j.d_stream_blocks = t.stream_blocks; j.d_fixups = t.fixups;
+    return j;
+}
+
+// Enqueue the whole decode of frames [f0, f1) on stream s.  d_coef is a buffer for (f1-f0) frames;
+// d_out receives (f1-f0) frames.  When prof != nullptr, events ev[0..4] bracket the stages.
+int enqueue_chunk(mjpeg423_b200_ctx* c, const Plan& plan, const Tables& t, const uint8_t* d_payload_origin,
+                  uint32_t f0, uint32_t f1, int16_t* d_coef, void* d_out, cudaStream_t s, cudaEvent_t* prof) {
+    EntropyJob j = make_job(plan, t, d_payload_origin, f0, f1);
+    const size_t frame_blocks = (size_t)3 * plan.nb;
+    int16_t* coef_origin = d_coef - (size_t)f0 * frame_blocks * 64;    // StreamDesc.block_base is plan-relative
+    if (prof) CU(cudaEventRecord(prof[0], s));
+    CU(launch_entropy_sync(j, s));
+    CU(launch_entropy_chain(j, s));
+    if (prof) CU(cudaEventRecord(prof[1], s));
+    CU(launch_entropy_write(j, c->d_quant, coef_origin, s));
+    if (prof) CU(cudaEventRecord(prof[2], s));
+    c->stats.kernel_launches += 3;
+    if (c->staged) {
+        const size_t nblk = (size_t)(f1 - f0) * frame_blocks;
+        int rc = c->samples.reserve(nblk * 64);
+        if (rc) return rc;
+        CU(launch_idct(d_coef, c->samples.as<uint8_t>(), nblk, s));
+        if (prof) CU(cudaEventRecord(prof[3], s));
+        CU(launch_colour(c->samples.as<uint8_t>(), d_out, f1 - f0, plan.W, plan.H, s));
+        c->stats.kernel_launches += 2;
+    } else {
+        if (prof) CU(cudaEventRecord(prof[3], s));
+        CU(launch_idct_colour(d_coef, d_out, f1 - f0, plan.W, plan.H, s));
+        c->stats.kernel_launches += 1;
+    }
+    if (prof) CU(cudaEventRecord(prof[4], s));
+    return MJPEG423_OK;
+}
+
+int accumulate_profile(mjpeg423_b200_ctx* c, cudaEvent_t* prof) {
+    CU(cudaEventSynchronize(prof[4]));
+    float a = 0, b = 0, d = 0, e = 0;
+    CU(cudaEventElapsedTime(&a, prof[0], prof[1]));
+    CU(cudaEventElapsedTime(&b, prof[1], prof[2]));
+    CU(cudaEventElapsedTime(&d, prof[2], prof[3]));
+    CU(cudaEventElapsedTime(&e, prof[3], prof[4]));
+    c->stats.entropy_sync_ms += a;
+    c->stats.entropy_write_ms += b;
+    if (c->staged) { c->stats.idct_ms += d; c->stats.colour_ms += e; }
+    c->stats.idct_colour_ms += d + e;
+    return MJPEG423_OK;
+}
+
+// After all chunks: fetch the fix-up counter and (optionally) check that every stream held nb blocks.
+int finish_stats(mjpeg423_b200_ctx* c, const Plan& plan, const Tables& t, cudaStream_t s) {
+    unsigned long long fix = 0;
+    CU(cudaMemcpyAsync(&fix, t.fixups, 8, cudaMemcpyDeviceToHost, s));
+    std::vector<uint32_t> blocks;
+    if (c->validate) {
+        blocks.resize(plan.streams.size());
+        CU(cudaMemcpyAsync(blocks.data(), t.stream_blocks, blocks.size() * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    c->stats.fixups = fix;
+    c->stats.segments = plan.f_seg0.back();
+    c->stats.payload_bytes = plan.stream_bytes;
+    c->stats.frames = plan.n;
+    for (size_t i = 0; i < blocks.size(); i++)
+        if (blocks[i] < plan.nb) {
+            set_error("stream " + std::to_string(i % 3) + " of frame " + std::to_string(plan.first + i / 3) + " holds " +
+                      std::to_string(blocks[i]) + " blocks, expected " + std::to_string(plan.nb));
+            return MJPEG423_E_STREAM;
+        }
+    return MJPEG423_OK;
+}
+
+}  // namespace
+
+extern "C" int mjpeg423_b200_upload(mjpeg423_b200_ctx* c, const uint8_t* mpg, size_t len, uint32_t first, uint32_t n) {
+    if (!c) return MJPEG423_E_ARG;
+    CU(cudaSetDevice(c->device));
+    c->have_plan = false;
+    MpgIndex idx;
+    int rc = parse_mpg(mpg, len, idx, false);
+    if (rc) return rc;
+    rc = build_plan(idx, first, n, c->plan);
+    if (rc) return rc;
+    if (n == 0) { c->have_plan = true; return MJPEG423_OK; }
+    rc = c->payload.reserve(c->plan.payload_len + 64);       // + look-ahead pad
+    if (rc) return rc;
+    Tables t;
+    rc = upload_tables(c, c->plan, t, c->s_compute);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->payload.p, mpg + c->plan.payload_off, c->plan.payload_len, cudaMemcpyHostToDevice, c->s_compute));
+    CU(cudaMemsetAsync(c->payload.as<uint8_t>() + c->plan.payload_len, 0, 64, c->s_compute));
+    CU(cudaStreamSynchronize(c->s_compute));
+    c->have_plan = true;
+    return MJPEG423_OK;
+}
+
+extern "C" int mjpeg423_b200_decode_resident(mjpeg423_b200_ctx* c, void* d_out) {
+    if (!c || !c->have_plan) { set_error("no resident job: call mjpeg423_b200_upload first"); return MJPEG423_E_ARG; }
+    CU(cudaSetDevice(c->device));
+    const Plan& plan = c->plan;
+    c->stats = mjpeg423_b200_stats{};
+    if (plan.n == 0) return MJPEG423_OK;
+    if (!d_out) return MJPEG423_E_ARG;
+    Tables t = tables_of(c, plan);
+    const size_t coef_frame = (size_t)3 * plan.nb * 128;
+    const uint32_t K = c->chunk_frames ? std::min(c->chunk_frames, plan.n) : auto_chunk(plan, (uint64_t)3 << 30, coef_frame);
+    const uint32_t nchunks = (plan.n + K - 1) / K;
+    const int nbuf = (nchunks > 1 && !c->profile) ? 2 : 1;
+    for (int i = 0; i < nbuf; i++) { int rc = c->coef[i].reserve((size_t)K * coef_frame); if (rc) return rc; }
+    cudaStream_t st[2] = {c->s_compute, c->s_aux};
+    cudaEvent_t ev_start = c->ev[0], ev_stop = c->ev[1], ev_fork = c->ev[2], ev_join = c->ev[3];
+    cudaEvent_t* prof = c->profile ? &c->ev[4] : nullptr;
+    CU(cudaMemsetAsync(t.fixups, 0, 8, st[0]));
+    CU(cudaEventRecord(ev_start, st[0]));
+    if (nbuf == 2) { CU(cudaEventRecord(ev_fork, st[0])); CU(cudaStreamWaitEvent(st[1], ev_fork, 0)); }
+    for (uint32_t ch = 0; ch < nchunks; ch++) {
+        const uint32_t f0 = ch * K, f1 = std::min(plan.n, f0 + K);
+        const int b = (int)(ch % nbuf);
+        int rc = enqueue_chunk(c, plan, t, c->payload.as<uint8_t>(), f0, f1, c->coef[b].as<int16_t>(),
+                               (uint8_t*)d_out + (size_t)f0 * plan.nb * 256, st[b], prof);
+        if (rc) return rc;
+        if (prof) { rc = accumulate_profile(c, prof); if (rc) return rc; }
+    }
+    if (nbuf == 2) { CU(cudaEventRecord(ev_join, st[1])); CU(cudaStreamWaitEvent(st[0], ev_join, 0)); }
+    CU(cudaEventRecord(ev_stop, st[0]));
+    int rc = finish_stats(c, plan, t, st[0]);
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ev_start, ev_stop));
+    c->stats.total_ms = ms;
+    return rc;
+}
+
+extern "C" int mjpeg423_b200_get_stats(mjpeg423_b200_ctx* c, mjpeg423_b200_stats* s) {
+    if (!c || !s) return MJPEG423_E_ARG;
+    *s = c->stats;
+    return MJPEG423_OK;
+}
+
+// ---- stage-level entry points on the resident job ------------------------------------------------------
+extern "C" int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* c, int16_t* d_coef) {
+    if (!c || !c->have_plan || !d_coef) return MJPEG423_E_ARG;
+    CU(cudaSetDevice(c->device));
+    const Plan& plan = c->plan;
+    c->stats = mjpeg423_b200_stats{};
+    if (plan.n == 0) return MJPEG423_OK;
+    Tables t = tables_of(c, plan);
+    EntropyJob j = make_job(plan, t, c->payload.as<uint8_t>(), 0, plan.n);
+    cudaStream_t s = c->s_compute;
+    CU(cudaMemsetAsync(t.fixups, 0, 8, s));
+    CU(cudaEventRecord(c->ev[0], s));
+    CU(launch_entropy_sync(j, s));
+    CU(launch_entropy_chain(j, s));
+    CU(cudaEventRecord(c->ev[2], s));
+    CU(launch_entropy_write(j, c->d_quant, d_coef, s));
+    CU(cudaEventRecord(c->ev[1], s));
+    c->stats.kernel_launches = 3;
+    int rc = finish_stats(c, plan, t, s);
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats.total_ms = ms;
+    CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[2])); c->stats.entropy_sync_ms = ms;
+    CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[1])); c->stats.entropy_write_ms = ms;
+    return rc;
+}
+
+namespace {
+template <class F>
+int timed_stage(mjpeg423_b200_ctx* c, float* slot, F&& launch) {
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = c->s_compute;
+    CU(cudaEventRecord(c->ev[0], s));
+    CU(launch(s));
+    CU(cudaEventRecord(c->ev[1], s));
+    CU(cudaEventSynchronize(c->ev[1]));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+    c->stats = mjpeg423_b200_stats{};
+    c->stats.total_ms = ms; c->stats.kernel_launches = 1; c->stats.frames = c->plan.n;
+    if (slot) *slot = ms;
+    return MJPEG423_OK;
+}
+}  // namespace
+
+extern "C" int mjpeg423_b200_resident_idct(mjpeg423_b200_ctx* c, const int16_t* d_coef, uint8_t* d_samples) {
+    if (!c || !c->have_plan || !d_coef || !d_samples) return MJPEG423_E_ARG;
+    const size_t nblk = (size_t)c->plan.n * 3 * c->plan.nb;
+    return timed_stage(c, &c->stats.idct_ms, [&](cudaStream_t s) { return launch_idct(d_coef, d_samples, nblk, s); });
+}
+extern "C" int mjpeg423_b200_resident_colour(mjpeg423_b200_ctx* c, const uint8_t* d_samples, void* d_out) {
+    if (!c || !c->have_plan || !d_samples || !d_out) return MJPEG423_E_ARG;
+    return timed_stage(c, &c->stats.colour_ms,
+                       [&](cudaStream_t s) { return launch_colour(d_samples, d_out, c->plan.n, c->plan.W, c->plan.H, s); });
+}
+extern "C" int mjpeg423_b200_resident_idct_colour(mjpeg423_b200_ctx* c, const int16_t* d_coef, void* d_out) {
+    if (!c || !c->have_plan || !d_coef || !d_out) return MJPEG423_E_ARG;
+    return timed_stage(c, &c->stats.idct_colour_ms, [&](cudaStream_t s) {
+        return launch_idct_colour(d_coef, d_out, c->plan.n, c->plan.W, c->plan.H, s);
+    });
+}
+
+// ---- end-to-end path: host .mpg -> (host | device) frames, chunked and overlapped ----------------------
+extern "C" int mjpeg423_b200_decode_frames(mjpeg423_b200_ctx* c, const uint8_t* mpg, size_t len, uint32_t first,
+                                           uint32_t n, void* out, int out_on_device) {
+    if (!c) return MJPEG423_E_ARG;
+    CU(cudaSetDevice(c->device));
+    MpgIndex idx;
+    int rc = parse_mpg(mpg, len, idx, false);
+    if (rc) return rc;
+    Plan plan;
+    rc = build_plan(idx, first, n, plan);
+    if (rc) return rc;
+    c->have_plan = false;                       // the resident tables are about to be overwritten
+    c->stats = mjpeg423_b200_stats{};
+    if (n == 0) return MJPEG423_OK;
+    if (!out) return MJPEG423_E_ARG;
+    Tables t;
+    rc = upload_tables(c, plan, t, c->s_in);
+    if (rc) return rc;
+    const size_t frame_bytes = (size_t)plan.nb * 256, coef_frame = (size_t)3 * plan.nb * 128;
+    const uint32_t K = c->chunk_frames ? std::min(c->chunk_frames, n) : auto_chunk(plan, (uint64_t)512 << 20, frame_bytes);
+    const uint32_t nchunks = (n + K - 1) / K;
+    // Largest compressed chunk.
+    size_t max_in = 0;
+    for (uint32_t ch = 0; ch < nchunks; ch++) {
+        const uint32_t f0 = ch * K, f1 = std::min(n, f0 + K);
+        max_in = std::max<size_t>(max_in, plan.frames[f1 - 1].off + plan.frames[f1 - 1].size - plan.frames[f0].off);
+    }
+    for (int i = 0; i < 2; i++) {
+        if ((rc = c->in_ring[i].reserve(max_in + 64))) return rc;
+        if (!out_on_device && (rc = c->out_ring[i].reserve((size_t)K * frame_bytes))) return rc;
+    }
+    if ((rc = c->coef[0].reserve((size_t)K * coef_frame))) return rc;
+    cudaEvent_t ev_start = c->ev[0], ev_stop = c->ev[1];
+    cudaEvent_t* ev_in = &c->ev[2];     // [2]: payload slot uploaded
+    cudaEvent_t* ev_comp = &c->ev[4];   // [2]: chunk decoded (payload slot + out slot consumed/produced)
+    cudaEvent_t* ev_out = &c->ev[6];    // [2]: out slot read back
+    cudaEvent_t* prof = c->profile ? &c->ev[8] : nullptr;
+    CU(cudaMemsetAsync(t.fixups, 0, 8, c->s_in));
+    CU(cudaEventRecord(ev_start, c->s_in));
+    CU(cudaStreamWaitEvent(c->s_compute, ev_start, 0));
+    for (uint32_t ch = 0; ch < nchunks; ch++) {
+        const uint32_t f0 = ch * K, f1 = std::min(n, f0 + K);
+        const int b = (int)(ch & 1);
+        const uint64_t in_off = plan.frames[f0].off;
+        const size_t in_len = plan.frames[f1 - 1].off + plan.frames[f1 - 1].size - in_off;
+        // upload: the slot is free once the chunk that used it two iterations ago has been decoded
+        if (ch >= 2) CU(cudaStreamWaitEvent(c->s_in, ev_comp[b], 0));
+        CU(cudaMemcpyAsync(c->in_ring[b].p, mpg + in_off, in_len, cudaMemcpyHostToDevice, c->s_in));
+        CU(cudaMemsetAsync(c->in_ring[b].as<uint8_t>() + in_len, 0, 64, c->s_in));
+        CU(cudaEventRecord(ev_in[b], c->s_in));
+        // decode
+        CU(cudaStreamWaitEvent(c->s_compute, ev_in[b], 0));
+        if (!out_on_device && ch >= 2) CU(cudaStreamWaitEvent(c->s_compute, ev_out[b], 0));
+        uint8_t* d_dst = out_on_device ? (uint8_t*)out + (size_t)f0 * frame_bytes : c->out_ring[b].as<uint8_t>();
+        const uint8_t* origin = c->in_ring[b].as<uint8_t>() - (in_off - plan.payload_off);
+        rc = enqueue_chunk(c, plan, t, origin, f0, f1, c->coef[0].as<int16_t>(), d_dst, c->s_compute, prof);
+        if (rc) return rc;
+        CU(cudaEventRecord(ev_comp[b], c->s_compute));
+        if (prof) { rc = accumulate_profile(c, prof); if (rc) return rc; }
+        // read back
+        if (!out_on_device) {
+            CU(cudaStreamWaitEvent(c->s_out, ev_comp[b], 0));
+            CU(cudaMemcpyAsync((uint8_t*)out + (size_t)f0 * frame_bytes, d_dst, (size_t)(f1 - f0) * frame_bytes,
+                               cudaMemcpyDeviceToHost, c->s_out));
+            CU(cudaEventRecord(ev_out[b], c->s_out));
+        }
+    }
+    cudaStream_t last = out_on_device ? c->s_compute : c->s_out;
+    CU(cudaEventRecord(ev_stop, last));
+    CU(cudaStreamSynchronize(last));
+    CU(cudaStreamSynchronize(c->s_compute));
+    rc = finish_stats(c, plan, t, c->s_compute);
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ev_start, ev_stop));
+    c->stats.total_ms = ms;
+    return rc;
+}
+
+// ---- memory helpers ------------------------------------------------------------------------------------
+extern "C" void* mjpeg423_b200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void mjpeg423_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+extern "C" void* mjpeg423_b200_device_alloc(mjpeg423_b200_ctx* c, size_t bytes) {
+    if (!c || cudaSetDevice(c->device) != cudaSuccess) return nullptr;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void mjpeg423_b200_device_free(mjpeg423_b200_ctx* c, void* p) {
+    if (c && p) { cudaSetDevice(c->device); cudaFree(p); }
+}
+extern "C" int mjpeg423_b200_memcpy_d2h(mjpeg423_b200_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c) return MJPEG423_E_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaStreamSynchronize(c->s_compute));
+    return MJPEG423_OK;
+}
+extern "C" int mjpeg423_b200_memcpy_h2d(mjpeg423_b200_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c) return MJPEG423_E_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->s_compute));
+    CU(cudaStreamSynchronize(c->s_compute));
+    return MJPEG423_OK;
+}
+extern "C" int mjpeg423_b200_sync(mjpeg423_b200_ctx* c) {
+    if (!c) return MJPEG423_E_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    return MJPEG423_OK;
+}
+extern "C" int mjpeg423_b200_hash_frames(mjpeg423_b200_ctx* c, const void* d_frames, uint64_t frame_bytes, uint32_t n,
+                                         uint64_t* hashes) {
+    if (!c || !hashes || (frame_bytes & 7)) return MJPEG423_E_ARG;
+    CU(cudaSetDevice(c->device));
+    int rc = c->misc.reserve((size_t)n * 8 + 8);
+    if (rc) return rc;
+    CU(launch_hash_frames(d_frames, frame_bytes, n, c->misc.as<unsigned long long>(), c->s_compute));
+    CU(cudaMemcpyAsync(hashes, c->misc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaStreamSynchronize(c->s_compute));
+    return MJPEG423_OK;
+}

@@ -1,0 +1,97 @@
+// runtime.h -- host runtime of libmjpeg423_b200: container walk, stream/tile tables, device buffers,
+// chunked multi-stream pipeline.  Internal header (the public surface is include/mjpeg423_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "mjpeg423_b200.h"
+
+namespace mj {
+
+// Device view of the entropy stage for one launch (one chunk of frames).  All table pointers are
+// already offset so that the indices stored in StreamDesc / TileDesc (which are relative to the whole
+// plan) address the right element.
+struct EntropyJob {
+    const uint8_t* d_payload = nullptr;          // address of plan.payload_off (may lie before the chunk's buffer)
+    const StreamDesc* d_streams = nullptr;       // plan-wide table
+    const TileDesc* d_sync_tiles = nullptr;      // first sync tile of the chunk
+    const TileDesc* d_write_tiles = nullptr;     // first write tile of the chunk
+    uint32_t stream_lo = 0, n_streams = 0;       // streams of the chunk (chain kernel: one CTA each)
+    uint32_t n_sync_tiles = 0, n_write_tiles = 0;
+    uint32_t *d_seg_entry = nullptr, *d_seg_exit = nullptr, *d_seg_cd = nullptr, *d_seg_first = nullptr; // plan-wide
+    uint32_t* d_stream_blocks = nullptr;         // plan-wide, per stream
+    unsigned long long* d_fixups = nullptr;
+};
+
+cudaError_t launch_entropy_sync(const EntropyJob& j, cudaStream_t s);
+cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s);
+cudaError_t launch_entropy_write(const EntropyJob& j, const int16_t* d_quant, int16_t* d_coef, cudaStream_t s);
+cudaError_t launch_idct(const int16_t* d_coef, uint8_t* d_samples, size_t n_blocks, cudaStream_t s);
+cudaError_t launch_colour(const uint8_t* d_samples, void* d_out, uint32_t n_frames, uint32_t W, uint32_t H,
+                          cudaStream_t s);
+cudaError_t launch_idct_colour(const int16_t* d_coef, void* d_out, uint32_t n_frames, uint32_t W, uint32_t H,
+                               cudaStream_t s);
+cudaError_t launch_hash_frames(const void* d_frames, uint64_t frame_bytes, uint32_t n, unsigned long long* d_hashes,
+                               cudaStream_t s);
+
+// ---- container (reader LIB/decoder/mjpeg423_decoder.c:33-38,94-107) -----------------
+struct FrameRec {
+    uint64_t off;          // file offset of the 16-byte frame header
+    uint32_t size, type, ysize, cbsize, crsize;
+};
+struct MpgIndex {
+    mjpeg423_b200_info info{};
+    std::vector<FrameRec> frames;
+};
+int parse_mpg(const uint8_t* mpg, size_t len, MpgIndex& idx, bool headers_only);
+
+// Host-side tables for frames [first, first+n).
+struct Plan {
+    uint32_t W = 0, H = 0, nb = 0, first = 0, n = 0;
+    uint64_t payload_off = 0, payload_len = 0;   // byte range of the file covered by the frames
+    std::vector<FrameRec> frames;
+    std::vector<StreamDesc> streams;             // 3 per frame: Y, Cb, Cr
+    std::vector<TileDesc> sync_tiles, write_tiles;
+    std::vector<uint32_t> f_sync0, f_write0, f_seg0;   // n+1 prefix tables per frame
+    uint64_t stream_bytes = 0;                   // sum of plane stream lengths
+};
+int build_plan(const MpgIndex& idx, uint32_t first, uint32_t n, Plan& plan);
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+}  // namespace mj
+
+// Device buffer with lazy growth.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct mjpeg423_b200_ctx {
+    int device = 0;
+    cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr, s_aux = nullptr;
+    // options
+    bool profile = false, staged = false, validate = true;
+    uint32_t chunk_frames = 0;
+    // quant tables (2 x 64 int16, natural order) on device
+    int16_t h_quant[128];
+    int16_t* d_quant = nullptr;
+    // resident job
+    mj::Plan plan;
+    bool have_plan = false;
+    DevBuf payload, tables, segs, coef[2], samples, stream_blocks, misc;
+    // staging for the host-buffer path
+    DevBuf in_ring[2], out_ring[2];
+    void* h_stage[2] = {nullptr, nullptr};
+    size_t h_stage_cap[2] = {0, 0};
+    cudaEvent_t ev[16] = {};
+    mjpeg423_b200_stats stats{};
+};

@@ -1,0 +1,182 @@
+/*
+ * mjpeg423_oracle.c -- CPU restatement of the MJPEG423 decode hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under mjpeg423-video-decoder-software_b200/ may link, import or call
+ * this file; it exists so tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg
+ * have an independent checker for the CUDA path.
+ *
+ * Parity status: PINNED.  The reference ships no golden vectors, so this
+ * restatement is pinned two ways: (1) against the known-answer vectors in BASELINE.md
+ * section 5 / tests/golden/kat.json, which were produced by running the unmodified
+ * reference functions; (2) against oracle/_ref/libmjpeg423_ref.so, i.e. the reference's
+ * own C files compiled in place by oracle/Makefile, on randomised inputs
+ * (tests/test_oracle.py).
+ *
+ * LIB/ below abbreviates /root/reference/core0/software/common/libs/mjpeg423/.
+ * All arithmetic is done on uint32_t and reinterpreted, so wrap-around is defined
+ * behaviour here even where the reference relies on -fwrapv.
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- tables: LIB/common/tables.c:13-42 (JPEG Annex K, natural order; zig-zag scan) ---- */
+const int16_t orc_Yquant[64] = {
+    16, 11, 10, 16, 24,  40,  51,  61,   12, 12, 14, 19, 26,  58,  60,  55,
+    14, 13, 16, 24, 40,  57,  69,  56,   14, 17, 22, 29, 51,  87,  80,  62,
+    18, 22, 37, 56, 68,  109, 103, 77,   24, 35, 55, 64, 81,  104, 113, 92,
+    49, 64, 78, 87, 103, 121, 120, 101,  72, 92, 95, 98, 112, 100, 103, 99};
+const int16_t orc_Cquant[64] = {
+    17, 18, 24, 47, 99, 99, 99, 99,  18, 21, 26, 66, 99, 99, 99, 99,
+    24, 26, 56, 99, 99, 99, 99, 99,  47, 66, 99, 99, 99, 99, 99, 99,
+    99, 99, 99, 99, 99, 99, 99, 99,  99, 99, 99, 99, 99, 99, 99, 99,
+    99, 99, 99, 99, 99, 99, 99, 99,  99, 99, 99, 99, 99, 99, 99, 99};
+
+/* zig-zag position -> natural (row*8+col) index, generated rather than typed in. */
+static uint8_t zz_nat[64];
+static pthread_once_t zz_once = PTHREAD_ONCE_INIT;
+static void zz_build(void) {
+    int r = 0, c = 0;
+    for (int k = 0; k < 64; k++) {
+        zz_nat[k] = (uint8_t)(r * 8 + c);
+        if ((r + c) & 1) {            /* moving down-left */
+            if (r == 7) c++; else if (c == 0) r++; else { r++; c--; }
+        } else {                      /* moving up-right */
+            if (c == 7) r++; else if (r == 0) c++; else { r--; c++; }
+        }
+    }
+}
+const uint8_t* orc_zigzag(void) { pthread_once(&zz_once, zz_build); return zz_nat; }
+
+/* ---- entropy decode: LIB/decoder/lossless_decode.c:60-135 ---- */
+/* MSB-first reader.  The reference keeps a 32-bit window that it tops up by whole bytes
+ * (update_buffer, :139-162); only the consumed-bit count matters for the result, so this
+ * reader simply indexes bits.  `peek` returns the next n (<=24) bits. */
+typedef struct { const uint8_t* p; uint64_t bit; } bitrd_t;
+static inline uint32_t peek(const bitrd_t* r, int n) {
+    const uint8_t* q = r->p + (r->bit >> 3);
+    uint32_t w = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+    w <<= (r->bit & 7);           /* <=7 bits dropped, 25 left: enough for header+15 via two peeks */
+    return n ? (w >> (32 - n)) : 0;
+}
+/* JPEG VLI sign extension, HUFF_EXTEND at :204, result truncated to DCTELEM as in huff_input_t. */
+static inline int16_t vli(uint32_t x, int s) {
+    if (x < (1u << (s - 1))) x += (0xFFFFFFFFu << s) + 1u;
+    return (int16_t)x;
+}
+/* Returns the number of bits consumed (test hook; the reference returns void). */
+uint64_t orc_lossless_decode(int num_blocks, const void* bitstream, int16_t* DCACq,
+                             const int16_t* quant, int P) {
+    const uint8_t* zz = orc_zigzag();
+    bitrd_t rd = {(const uint8_t*)bitstream, 0};
+    int16_t cur = 0;                                   /* :73 DC predictor, DCTELEM wide */
+    if (!P) memset(DCACq, 0, (size_t)num_blocks * 128); /* :77-78 */
+    for (int b = 0; b < num_blocks; b++) {
+        int16_t* pe = DCACq + (size_t)b * 64;
+        /* DC symbol: input_DC :210-224 */
+        int s = (int)peek(&rd, 4); rd.bit += 4;
+        int16_t e = 0;
+        if (s) { e = vli(peek(&rd, s), s); rd.bit += s; }
+        if (P) pe[0] = (int16_t)(pe[0] + e * quant[0]);            /* :90-92 */
+        else { cur = (int16_t)(cur + e); pe[0] = (int16_t)(cur * quant[0]); } /* :93-96 */
+        /* AC symbols: input_AC :227-246, loop :101-133.  index is uint8_t in the reference. */
+        uint8_t idx = 1;
+        for (;;) {
+            int run = (int)peek(&rd, 4);
+            rd.bit += 4;
+            s = (int)peek(&rd, 4);
+            rd.bit += 4;
+            if (s == 0) {                       /* e == 0 <=> size == 0 */
+                if (run == 15) { idx = (uint8_t)(idx + 16); continue; } /* ZRL :107-110 */
+                break;                          /* END :111-114 (any run != 15) */
+            }
+            e = vli(peek(&rd, s), s); rd.bit += s;
+            idx = (uint8_t)(idx + run);
+            if (idx < 64) {                     /* reference indexes unchecked; conforming streams stay < 64 */
+                int n = zz[idx];
+                if (P) pe[n] = (int16_t)(pe[n] + e * quant[n]);     /* :121-123 */
+                else   pe[n] = (int16_t)(e * quant[n]);             /* :124-126 */
+            }
+            if (idx >= 63) break;               /* :130 */
+            idx++;
+        }
+    }
+    return rd.bit;
+}
+
+/* ---- 8x8 IDCT: LIB/decoder/idct.c:22-181, constants LIB/common/dct_math.h:48-76 ---- */
+#define C0_298 2446u
+#define C0_390 3196u
+#define C0_541 4433u
+#define C0_765 6270u
+#define C0_899 7373u
+#define C1_175 9633u
+#define C1_501 12299u
+#define C1_847 15137u
+#define C1_961 16069u
+#define C2_053 16819u
+#define C2_562 20995u
+#define C3_072 25172u
+static inline int32_t asr_round(uint32_t x, int n) {   /* DESCALE, dct_math.h:48 */
+    return (int32_t)(x + (1u << (n - 1))) >> n;
+}
+/* One LL&M 8-point inverse pass on in[0..7] (idct.c:46-97 == :123-168); out[k] are the
+ * un-descaled sums in output order 0..7. */
+static inline void llm8(const int32_t in[8], uint32_t out[8]) {
+    uint32_t a2 = (uint32_t)in[2], a6 = (uint32_t)in[6];
+    uint32_t z1 = (a2 + a6) * C0_541;
+    uint32_t t2 = z1 - a6 * C1_847;
+    uint32_t t3 = z1 + a2 * C0_765;
+    uint32_t t0 = ((uint32_t)in[0] + (uint32_t)in[4]) << 13;
+    uint32_t t1 = ((uint32_t)in[0] - (uint32_t)in[4]) << 13;
+    uint32_t e0 = t0 + t3, e3 = t0 - t3, e1 = t1 + t2, e2 = t1 - t2;
+    uint32_t o0 = (uint32_t)in[7], o1 = (uint32_t)in[5], o2 = (uint32_t)in[3], o3 = (uint32_t)in[1];
+    uint32_t y1 = o0 + o3, y2 = o1 + o2, y3 = o0 + o2, y4 = o1 + o3;
+    uint32_t y5 = (y3 + y4) * C1_175;
+    o0 *= C0_298; o1 *= C2_053; o2 *= C3_072; o3 *= C1_501;
+    y1 = 0u - y1 * C0_899; y2 = 0u - y2 * C2_562;
+    y3 = y5 - y3 * C1_961; y4 = y5 - y4 * C0_390;
+    o0 += y1 + y3; o1 += y2 + y4; o2 += y2 + y3; o3 += y1 + y4;
+    out[0] = e0 + o3; out[7] = e0 - o3;
+    out[1] = e1 + o2; out[6] = e1 - o2;
+    out[2] = e2 + o1; out[5] = e2 - o1;
+    out[3] = e3 + o0; out[4] = e3 - o0;
+}
+void orc_idct(const int16_t* DCAC, uint8_t* block) {
+    int32_t ws[64], v[8];
+    uint32_t o[8];
+    for (int c = 0; c < 8; c++) {              /* pass 1, columns: descale by CONST_BITS-PASS1_BITS = 11 */
+        for (int r = 0; r < 8; r++) v[r] = DCAC[r * 8 + c];
+        llm8(v, o);
+        for (int r = 0; r < 8; r++) ws[r * 8 + c] = asr_round(o[r], 11);
+    }
+    for (int r = 0; r < 8; r++) {              /* pass 2, rows: descale by 13+2+3 = 18, clamp (:20) */
+        llm8(ws + r * 8, o);
+        for (int c = 0; c < 8; c++) {
+            int32_t t = asr_round(o[c], 18);
+            block[r * 8 + c] = (uint8_t)(t < 0 ? 0 : (t > 255 ? 255 : t));
+        }
+    }
+}
+
+/* ---- colour: LIB/decoder/ycbcr_to_rgb.c:26-49; pixel layout LIB/common/mjpeg423_types.h:56-61 ---- */
+static inline uint32_t sat14(int32_t t) {          /* NORMALIZE_RGB :19 */
+    if (t < 0) return 0;
+    t >>= 14;
+    return t > 255 ? 255u : (uint32_t)t;
+}
+void orc_ycbcr_to_rgb(int h, int w, uint32_t w_size, const uint8_t* Y, const uint8_t* Cb,
+                      const uint8_t* Cr, uint8_t* rgb /* BGRA bytes */) {
+    for (int y = 0; y < 8; y++) {
+        uint8_t* dst = rgb + ((size_t)(h + y) * w_size + (size_t)w) * 4;
+        for (int x = 0; x < 8; x++) {
+            int32_t cb = (int32_t)Cb[y * 8 + x] - 128, cr = (int32_t)Cr[y * 8 + x] - 128;
+            int32_t yy = (int32_t)Y[y * 8 + x] << 14;
+            dst[4 * x + 0] = (uint8_t)sat14(yy + 29032 * cb);
+            dst[4 * x + 1] = (uint8_t)sat14(yy - 5638 * cb - 11700 * cr);
+            dst[4 * x + 2] = (uint8_t)sat14(yy + 22970 * cr);
+            dst[4 * x + 3] = 0;
+        }
+    }
+}
