@@ -158,7 +158,7 @@ k_entropy_chain(const uint8_t* __restrict__ payload, const StreamDesc* __restric
 
     // 1. make the chain exact: entry[0] = 0, entry[i] = exit[i-1].
     uint32_t nfix = 0;
-    for (;;) {
+    for (uint32_t sweep = 0; sweep <= sd.nseg + 1; sweep++) {   // converges in <= nseg sweeps; bound it anyway
         int changed = 0;
         for (uint32_t i = t; i < sd.nseg; i += CHAIN_TPB) {
             uint32_t E = i ? v_exit[i - 1] : 0u;

@@ -77,6 +77,8 @@ int build_plan(const MpgIndex& idx, uint32_t first, uint32_t n, Plan& plan) {
     }
     if ((uint64_t)n * 3 * plan.nb >= 0xFFFFFFFFull) { set_error("too many blocks in one plan"); return MJPEG423_E_ARG; }
     plan.frames.assign(idx.frames.begin() + first, idx.frames.begin() + first + n);
+    for (const FrameRec& r : plan.frames)
+        if (r.type != 0) { set_error("P frames are not supported by the batched path yet"); return MJPEG423_E_PFRAME; }
     plan.payload_off = plan.frames.front().off;
     plan.payload_len = plan.frames.back().off + plan.frames.back().size - plan.payload_off;
     plan.streams.reserve((size_t)n * 3);
