@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- decoded frames/s of the MJPEG423 hot path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 1080p|4k|480p|1080p-8192]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's own C functions on the host cores
+
+One "step" = one pass of the hot path (entropy decode -> dequantise -> IDCT -> YCbCr->BGRA) over the
+rank's whole batch of frames.  `value` is timed with the compressed stream already resident in HBM
+(CUDA events on the library's streams, max over ranks); `e2e` goes through the public host-buffer call
+(mjpeg423_b200_decode_frames): pinned .mpg in, pinned BGRA frames out, H2D and D2H inside the timed
+region.  Frames are independent intra frames, so ranks shard by frame range with no collective
+("weak": every rank decodes its own `frames` frames; the 1080p-8192 workload is the fixed-total variant).
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (W, H, frames per GPU (weak) or total (strong), unique pictures, noise amplitude, quant, strong?)
+    "480p": (640, 480, 4800, 64, 16, "default", False),         # BASELINE configs[0]/[1] content, longer
+    "1080p": (1920, 1080, 2000, 64, 16, "default", False),      # BASELINE configs[2]: the headline config
+    "4k": (3840, 2160, 256, 16, 256, "default", False),         # BASELINE configs[3]: dense, entropy-bound
+    "4k-q1": (3840, 2160, 128, 8, 256, "ones", False),          # configs[3] extreme: all-ones quant tables
+    "1080p-8192": (1920, 1080, 8192, 64, 16, "default", True),  # BASELINE configs[4]: fixed total, sharded
+}
+HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        # the first samples may predate the load; take the median of the upper half
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_stream(wl: str, frames: int, nthreads: int):
+    from mjpeg423_b200 import synth
+    W, H, _, uniq, amp, quant, _ = WORKLOADS[wl]
+    q = np.ones(64, np.int16) if quant == "ones" else None
+    uniq = min(uniq, frames)
+    mpg = synth.synth_mpg(W, H, frames, uniq, amp, 0, q, q, nthreads=nthreads)
+    return mpg, uniq, q
+
+
+def reference_arm(args, rank: int, world: int):
+    """The reference's own lossless_decode/idct/ycbcr_to_rgb (oracle/_ref, compiled from /root/reference)
+    or, if that did not travel, the C restatement -- on all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import oracle
+    chk = oracle.best()
+    W, H, _, uniq, amp, quant, _ = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    fps_guess = {"480p": 170.0, "1080p": 21.0, "4k": 4.0, "4k-q1": 3.0, "1080p-8192": 21.0}[args.workload] * cores
+    n = int(max(cores, min(64 * 8, fps_guess * args.ref_seconds)))
+    mpg, uniq, q = make_stream(args.workload, n, cores)
+    for _ in range(args.warmup):
+        chk.decode_mpg(mpg, 0, min(n, cores), yq=q, cq=q, nthreads=cores)
+    stage = np.zeros(3)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        chk.decode_mpg(mpg, 0, n, yq=q, cq=q, nthreads=cores, stage_secs=stage)
+    dt = time.perf_counter() - t0
+    fps = n * args.steps / dt
+    sample = f"{n} frames {W}x{H} per step ({uniq} unique pictures cycled), {cores} threads, contiguous frame range each"
+    line = {
+        "impl": "reference", "metric": "decoded frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": args.workload, "width": W, "height": H, "frames_per_step": n, "noise_amp": amp,
+                   "quant": quant, "host": "cpu"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": chk.kind, "sample": sample,
+                         "stage_share": {k: float(v / stage.sum()) for k, v in zip(("entropy", "idct", "colour"), stage)}},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="override frames per GPU (weak) / total (strong)")
+    ap.add_argument("--e2e-frames", type=int, default=0, help="frames per end-to-end step (0 = auto, ~4 GB of output)")
+    ap.add_argument("--ref-seconds", type=float, default=3.0, help="wall seconds per reference-arm step")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-seconds of work for the cpu_baseline sample")
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import mjpeg423_b200
+    from mjpeg423_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the host arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    W, H, frames, uniq, amp, quant, strong = WORKLOADS[args.workload]
+    if args.frames:
+        frames = args.frames
+    if strong:
+        lo, hi = frames * rank // world, frames * (rank + 1) // world
+        my_frames = hi - lo
+    else:
+        my_frames = frames
+    cores = os.cpu_count() or 1
+    mpg, uniq, q = make_stream(args.workload, my_frames, max(1, cores // world))
+    frame_bytes = W * H * 4
+    P = W * H
+
+    dec = mjpeg423_b200.Decoder(local_rank)
+    if q is not None:
+        dec.set_quant(q, q)
+    info = dec.upload(mpg)
+    d_out = dec.device_alloc(my_frames * frame_bytes)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness gate (untimed): every frame of this rank against the CPU oracle ------------------
+    verified = None
+    if not args.no_verify:
+        from oracle import oracle
+        chk = oracle.best()
+        dec.decode_resident(d_out)
+        got = dec.hash_frames(d_out, frame_bytes, my_frames)
+        want_u = api.frame_hash_host(chk.decode_mpg(mpg, 0, uniq, yq=q, cq=q, nthreads=max(1, cores // world)))
+        want = want_u[np.arange(my_frames) % uniq]
+        if not np.array_equal(got, want):
+            bad = int(np.flatnonzero(got != want)[0])
+            raise SystemExit(f"rank {rank}: frame {bad} differs from the {chk.kind} oracle -- refusing to report a number")
+        first = dec.to_host(d_out, frame_bytes).reshape(H, W, 4)
+        assert np.array_equal(first, chk.decode_mpg(mpg, 0, 1, yq=q, cq=q)[0])
+        verified = f"{my_frames} frames/rank: per-frame 64-bit checksum == {chk.kind} oracle; frame 0 byte-compared"
+
+    # ---- device-resident throughput -------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        dec.decode_resident(d_out)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev_ms, launches = 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dec.decode_resident(d_out)
+        st = dec.stats()
+        ev_ms += st["total_ms"]
+        launches += st["kernel_launches"]
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    payload_bytes = st["payload_bytes"]
+
+    # ---- per-stage times (profiled step: events between the kernels, stages serialised) ---------------------
+    dec.set_option(api.OPT_PROFILE, 1)
+    dec.decode_resident(d_out)
+    dec.decode_resident(d_out)
+    ps = dec.stats()
+    dec.set_option(api.OPT_PROFILE, 0)
+
+    # ---- end to end: pinned host .mpg -> pinned host frames through the public call ----------------------------
+    e2e_frames = args.e2e_frames or int(max(1, min(my_frames, (4 << 30) // frame_bytes)))
+    fr_off = 20
+    for _ in range(e2e_frames):
+        fr_off += int(mpg[fr_off:fr_off + 4].view("<u4")[0])
+    h2d_bytes = fr_off - 20
+    pin_in = dec.pinned(mpg.size + 64)
+    pin_in.array[:mpg.size] = mpg
+    pin_out = dec.pinned(e2e_frames * frame_bytes)
+    e2e_steps = max(2, min(args.steps, 5))
+    dec.decode_frames(pin_in.array[:mpg.size], 0, e2e_frames, out=pin_out)     # warm-up (allocates rings)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dec.decode_frames(pin_in.array[:mpg.size], 0, e2e_frames, out=pin_out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if not args.no_verify:
+        tail = pin_out.array[-frame_bytes:].reshape(1, H, W, 4)
+        assert api.frame_hash_host(tail)[0] == want[e2e_frames - 1], "end-to-end output differs from the oracle"
+
+    # ---- reduce over ranks ----------------------------------------------------------------------------------------
+    t = torch.tensor([ev_ms, wall_ms, e2e_s], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(my_frames), float(launches), float(e2e_frames)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ev_ms_max, wall_ms_max, e2e_s_max = (float(x) for x in t.tolist())
+    total_frames, total_launches, total_e2e_frames = (float(x) for x in cnt.tolist())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        fps = total_frames * args.steps / (ev_ms_max / 1e3)
+        Cbar = payload_bytes / my_frames
+        n = my_frames
+        stage = {
+            # ALGORITHMIC bytes per launch: C = compressed bytes, P = pixels per frame
+            "entropy_sync": {"ms": ps["entropy_sync_ms"], "bytes": payload_bytes, "kernels": "k_entropy_sync + k_entropy_chain"},
+            "entropy_write": {"ms": ps["entropy_write_ms"], "bytes": payload_bytes + 6 * P * n, "kernels": "k_entropy_write"},
+            "idct_colour": {"ms": ps["idct_colour_ms"], "bytes": 10 * P * n, "kernels": "k_idct_colour"},
+        }
+        for s in stage.values():
+            s["GBs"] = s["bytes"] / max(s["ms"], 1e-9) / 1e6
+            s["frac_of_hbm_peak"] = s["GBs"] / peak
+        dom = max(stage, key=lambda k: stage[k]["ms"])
+        roofline = {"bound": "hbm", "kernel": stage[dom]["kernels"], "achieved": stage[dom]["GBs"], "peak": peak,
+                    "unit": "GB/s", "frac": stage[dom]["GBs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": stage[dom]["bytes"],
+                    "launch_ms": stage[dom]["ms"],
+                    "pipeline_headline": {"bytes_per_frame": Cbar + 4 * P, "GBs": fps / world * (Cbar + 4 * P) / 1e9,
+                                          "frac": fps / world * (Cbar + 4 * P) / 1e9 / peak}}
+        cpu_baseline = None
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import oracle
+            chk = oracle.best()
+            est = {"480p": 170.0, "1080p": 21.0, "4k": 4.0, "4k-q1": 3.0, "1080p-8192": 21.0}[args.workload]
+            ncpu = int(max(cores, min(my_frames, est * args.cpu_seconds)))
+            secs = np.zeros(3)
+            t0 = time.perf_counter()
+            chk.decode_mpg(mpg, 0, ncpu, yq=q, cq=q, nthreads=cores, stage_secs=secs)
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": ncpu / dt, "unit": "frames/s", "cores": cores, "kind": chk.kind,
+                            "sample": f"first {ncpu} frames of the same stream, {cores} threads, contiguous frame range each, "
+                                      f"{dt:.2f} s wall",
+                            "per_core": ncpu / secs.sum(),
+                            "stage_share": {k: float(v / secs.sum()) for k, v in zip(("entropy", "idct", "colour"), secs)}}
+        line = {
+            "metric": "decoded frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": args.workload, "width": W, "height": H, "frames_per_gpu": my_frames,
+                       "unique_pictures": uniq, "noise_amp": amp, "quant": quant,
+                       "compressed_bytes_per_frame": Cbar, "bits_per_pixel": 8 * Cbar / P,
+                       "l2": "inputs larger than L2 (bitstream %.0f MB, output %.1f GB per GPU per step)" %
+                             (payload_bytes / 1e6, my_frames * frame_bytes / 1e9),
+                       "parallelism": f"frame-range x{world}, no collective", "timing": "cuda events, max over ranks",
+                       "wall_ms_per_step": wall_ms_max / args.steps, "verified": verified},
+            "clocks": clocks,
+            "e2e": {"value": total_e2e_frames * e2e_steps / e2e_s_max, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(e2e_frames * frame_bytes), "frames_per_step": e2e_frames, "steps": e2e_steps,
+                    "GBs_d2h": total_e2e_frames / world * e2e_steps * frame_bytes / e2e_s_max / 1e9,
+                    "api": "mjpeg423_b200_decode_frames (pinned host in/out)"},
+            "gpu_launches": int(total_launches),
+            "roofline": roofline,
+            "stages": stage,
+            "segments": {"per_step": ps["segments"], "chain_fixups": ps["fixups"]},
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    pin_in.free()
+    pin_out.free()
+    dec.device_free(d_out)
+    dec.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
