@@ -278,10 +278,13 @@ def main():
         Cbar = payload_bytes / my_frames
         n = my_frames
         stage = {
-            # ALGORITHMIC bytes per launch: C = compressed bytes, P = pixels per frame
-            "entropy_sync": {"ms": ps["entropy_sync_ms"], "bytes": payload_bytes, "kernels": "k_entropy_sync + k_entropy_chain"},
-            "entropy_write": {"ms": ps["entropy_write_ms"], "bytes": payload_bytes + 6 * P * n, "kernels": "k_entropy_write"},
-            "idct_colour": {"ms": ps["idct_colour_ms"], "bytes": 10 * P * n, "kernels": "k_idct_colour"},
+            # ALGORITHMIC bytes per launch: C = compressed bytes, P = pixels per frame,
+            # 3*nb = P*3/64 blocks per frame; the block index is 6 bytes per block
+            "entropy_sync": {"ms": ps["sync_ms"], "bytes": payload_bytes, "kernels": "k_entropy_sync"},
+            "entropy_chain": {"ms": ps["chain_ms"], "bytes": 16 * ps["segments"], "kernels": "k_entropy_chain"},
+            "entropy_index": {"ms": ps["index_ms"], "bytes": payload_bytes + 6 * (3 * P // 64) * n, "kernels": "k_entropy_index"},
+            "decode_fused": {"ms": ps["decode_ms"], "bytes": payload_bytes + (6 * (3 * P // 64) + 4 * P) * n,
+                             "kernels": "k_decode_fused"},
         }
         for s in stage.values():
             s["GBs"] = s["bytes"] / max(s["ms"], 1e-9) / 1e6

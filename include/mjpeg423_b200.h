@@ -108,13 +108,15 @@ typedef struct {
 
 typedef struct {
     /* CUDA-event times (ms) of the most recent decode on this context, measured on the library's
-     * compute stream.  Stage times are only collected when profiling is on (set_option PROFILE 1),
-     * because the extra events serialise the stages. */
+     * streams.  total_ms is always collected; the per-kernel times only when profiling is on
+     * (set_option PROFILE 1), because the extra events serialise the kernels. */
     float total_ms;              /* whole device-side decode (all kernels of the call) */
-    float entropy_sync_ms;       /* speculative parse + merge + chain kernels */
-    float entropy_write_ms;      /* coefficient write kernel */
-    float idct_colour_ms;        /* fused IDCT + colour kernel (or idct_ms + colour_ms when staged) */
-    float idct_ms, colour_ms;
+    float sync_ms;               /* k_entropy_sync: speculative parse + merge */
+    float chain_ms;              /* k_entropy_chain: chain fix-up + scans */
+    float index_ms;              /* k_entropy_index: per-block bit positions and DC levels */
+    float decode_ms;             /* k_decode_fused (default) or k_decode_coef (staged modes) */
+    float idct_colour_ms;        /* k_idct_colour (staged mode 1) */
+    float idct_ms, colour_ms;    /* k_idct, k_colour (staged mode 2) */
     uint64_t kernel_launches;    /* kernels launched by the call */
     uint64_t payload_bytes;      /* compressed bytes consumed (sum of plane streams) */
     uint64_t segments, fixups;   /* bitstream segments / segments re-parsed by the chain kernel */
@@ -123,7 +125,9 @@ typedef struct {
 
 enum {
     MJPEG423_OPT_PROFILE      = 1,  /* 0/1: collect per-stage event times */
-    MJPEG423_OPT_STAGED       = 2,  /* 0: fused IDCT+colour kernel (default); 1: separate idct and colour kernels */
+    MJPEG423_OPT_STAGED       = 2,  /* 0: one fused decode kernel, bitstream -> BGRA (default; intra-only ranges);
+                                       1: coefficient planes in HBM + fused IDCT/colour kernel (used automatically
+                                          when the range holds P frames); 2: entropy, IDCT and colour kernels separate */
     MJPEG423_OPT_CHUNK_FRAMES = 3,  /* frames per pipeline chunk in the host-buffer path (0 = auto) */
     MJPEG423_OPT_VALIDATE     = 4   /* 0/1: check every stream decoded exactly num_blocks blocks (default 1) */
 };
@@ -173,8 +177,9 @@ int   mjpeg423_b200_memcpy_d2h(mjpeg423_b200_ctx* ctx, void* dst, const void* d_
 int   mjpeg423_b200_memcpy_h2d(mjpeg423_b200_ctx* ctx, void* d_dst, const void* src, size_t bytes);
 int   mjpeg423_b200_sync(mjpeg423_b200_ctx* ctx);
 int   mjpeg423_b200_device_count(void);
-/* 64-bit FNV-1a hash of every frame of a device-resident output (n x frame_bytes), computed on the GPU;
- * hashes (n x uint64) is host memory.  Used by the bench for whole-batch bit-exactness checks. */
+/* Position-mixed 64-bit checksum of every frame of a device-resident output (n x frame_bytes), computed
+ * on the GPU: sum over 8-byte words w_i of splitmix64(w_i ^ (i+1)*0x9E3779B97F4A7C15).  hashes (n x uint64)
+ * is host memory.  Used by the bench for whole-batch bit-exactness checks. */
 int   mjpeg423_b200_hash_frames(mjpeg423_b200_ctx* ctx, const void* d_frames, uint64_t frame_bytes, uint32_t n,
                                 uint64_t* hashes);
 

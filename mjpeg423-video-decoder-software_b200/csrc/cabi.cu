@@ -44,7 +44,7 @@ mjpeg423_b200_ctx* shim_ctx() {
 }
 
 // Scratch device buffers of the shims.
-DevBuf s_in, s_mid, s_out, s_tab, s_seg;
+DevBuf s_in, s_mid, s_out, s_tab, s_seg, s_idx;
 
 int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitstream, size_t len, int16_t* DCACq,
                          const int16_t* quant, int P) {
@@ -55,7 +55,7 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     StreamDesc sd{};
     sd.byte_off = 0; sd.byte_len = (uint32_t)len; sd.nb = (uint32_t)num_blocks; sd.seg_base = 0;
     sd.nseg = std::max<uint32_t>(1, ((uint32_t)len + SEG_BYTES - 1) / SEG_BYTES);
-    sd.block_base = 0; sd.quant_id = 0; sd.ptype = P ? 1 : 0;
+    sd.block_base = 0; sd.prev_base = 0; sd.quant_id = 0; sd.ptype = P ? 1 : 0;   // P: accumulate in place
     std::vector<TileDesc> sync_tiles, write_tiles;
     for (uint32_t s0 = 0; s0 < sd.nseg; s0 += ENT_TPB - 1) sync_tiles.push_back({0u, s0});
     for (uint32_t s0 = 0; s0 < sd.nseg; s0 += ENT_TPB) write_tiles.push_back({0u, s0});
@@ -65,6 +65,7 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     if ((rc = s_in.reserve(len + 64))) return rc;
     if ((rc = s_tab.reserve(256 + 256 + b_sync + b_write))) return rc;
     if ((rc = s_seg.reserve((size_t)sd.nseg * 16 + 64))) return rc;
+    if ((rc = s_idx.reserve((size_t)num_blocks * 6 + 64))) return rc;
     if ((rc = s_mid.reserve(coef_bytes))) return rc;
     uint8_t* tab = s_tab.as<uint8_t>();
     int16_t* d_q = reinterpret_cast<int16_t*>(tab);                  // 128 int16 (table 0 used)
@@ -88,10 +89,15 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     j.d_seg_first = seg + 3 * (size_t)sd.nseg;
     j.d_stream_blocks = seg + 4 * (size_t)sd.nseg;
     j.d_fixups = reinterpret_cast<unsigned long long*>(seg + 4 * (size_t)sd.nseg + 2);
+    j.d_blk_pos = s_idx.as<uint32_t>();
+    j.d_blk_dc = reinterpret_cast<int16_t*>(s_idx.as<uint32_t>() + num_blocks);
+    uint32_t* d_ids = reinterpret_cast<uint32_t*>(tab + 256 + 128);     // one id: stream 0
+    CUX(cudaMemsetAsync(d_ids, 0, 4, s));
     CUX(cudaMemsetAsync(j.d_fixups, 0, 8, s));
     CUX(launch_entropy_sync(j, s));
     CUX(launch_entropy_chain(j, s));
-    CUX(launch_entropy_write(j, d_q, s_mid.as<int16_t>(), s));
+    CUX(launch_entropy_index(j, s));
+    CUX(launch_decode_coef(j, d_ids, 1, sd.nb, d_q, s_mid.as<int16_t>(), s));
     CUX(cudaMemcpyAsync(DCACq, s_mid.p, coef_bytes, cudaMemcpyDeviceToHost, s));
     CUX(cudaStreamSynchronize(s));
     return MJPEG423_OK;

@@ -21,6 +21,7 @@ constexpr int ENT_TPB = 128;                   // threads per CTA in the entropy
 constexpr int MIN_BLOCK_BITS = 12;             // DC size 0 + END
 constexpr uint32_t RUNAWAY_BITS = 8192;        // parse guard for non-conforming / speculative garbage
 constexpr uint32_t MAX_STREAM_BYTES = 1u << 28; // bit positions are 32-bit
+constexpr uint32_t NO_BLOCK = 0xFFFFFFFFu;       // block index entry of a block the stream does not contain
 
 // One plane bitstream of one frame (built by the host from the 16-byte frame headers,
 // LIB/decoder/mjpeg423_decoder.c:94-107).
@@ -31,6 +32,8 @@ struct StreamDesc {
     uint32_t seg_base;     // index of this stream's first segment in the per-segment arrays
     uint32_t nseg;         // ceil(byte_len / SEG_BYTES), at least 1
     uint32_t block_base;   // index (in 64-coefficient blocks) of this plane in the coefficient buffer
+    uint32_t prev_base;    // P frames: block index of the same plane of the previous frame (the state
+                           // the deltas are added to, LIB/decoder/lossless_decode.c:90-92,121-123)
     uint16_t quant_id;     // 0 = luminance table, 1 = chrominance table
     uint16_t ptype;        // 0 = I frame (zero-fill, DC differential), 1 = P frame (accumulate)
 };
@@ -81,44 +84,108 @@ __device__ __forceinline__ int vli_extend(uint32_t amp, int size) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Block parser shared by every entropy kernel so that the speculative, merge and write passes follow
-// the SAME trajectory function.  Parses one block starting at r (positioned on a DC symbol) and
-// returns the number of bits consumed.  Sink::dc(e) / Sink::ac(zigzag_index, e) receive the symbols.
+// Symbol stepper shared by every segment-parallel pass (speculative parse, merge, chain re-parse,
+// block index) so that they all follow ONE trajectory function.  The passes run a single flat loop,
+// one symbol per iteration for every lane, with the DC/AC distinction and the block-end test
+// predicated -- lanes of a warp stay converged however their blocks are laid out.
 //   DC symbol  input_DC  LIB/decoder/lossless_decode.c:210-224  (4-bit size + amplitude)
 //   AC symbol  input_AC  :227-246 (4-bit run, 4-bit size, amplitude); size 0: run 15 = ZRL else END
 //   block loop :101-133; `index` is uint8_t there and wraps, so it does here.
-// max_bits bounds the parse on non-conforming input (memory safety; conforming blocks are <= 1212 bits).
+// A block is also ended when it has consumed `budget` bits: memory safety on non-conforming input and
+// on speculative garbage (conforming blocks are <= 1212 bits).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_budget(uint32_t blk_start, uint32_t total_bits) {
+    return min(RUNAWAY_BITS, total_bits - blk_start);
+}
+
+struct Parser {
+    BitReader r;
+    uint32_t pos;          // bit position of the next symbol
+    uint32_t blk_start;    // bit position of the current block's DC symbol
+    uint32_t budget;       // block_budget(blk_start)
+    uint32_t idx;          // zig-zag index of the next AC coefficient
+    bool is_dc;            // next symbol is a DC symbol (= we are at a block start)
+
+    __device__ __forceinline__ void start(const uint8_t* base, uint32_t bitpos, uint32_t total_bits) {
+        r.init(base, bitpos);
+        pos = blk_start = bitpos;
+        budget = block_budget(bitpos, total_bits);
+        idx = 1;
+        is_dc = true;
+    }
+    // Consume one symbol.  Returns true when it ended the block (the parser is then positioned on the
+    // next block's DC symbol).  dc_e receives the DC amplitude when the symbol was a DC symbol, else 0.
+    __device__ __forceinline__ bool step(uint32_t total_bits, int& dc_e) {
+        r.refill();
+        const uint32_t t = r.top();
+        const uint32_t hdr = is_dc ? 4u : 8u;
+        const uint32_t rs = t >> (32u - hdr);
+        const uint32_t size = rs & 15u, run = rs >> 4;          // run is garbage-free: rs < 16 for a DC symbol
+        const uint32_t len = hdr + size;
+        r.skip((int)len);
+        pos += len;
+        bool end;
+        dc_e = 0;
+        if (is_dc) {
+            if (size) dc_e = vli_extend((t << 4) >> (32u - size), (int)size);
+            is_dc = false;
+            idx = 1;
+            end = false;
+        } else if (size == 0) {
+            end = run != 15u;                   // END (any run but 15) / ZRL
+            idx = (idx + 16u) & 255u;
+        } else {
+            idx = (idx + run) & 255u;
+            end = idx >= 63u;
+            idx++;
+        }
+        end |= (pos - blk_start) >= budget;
+        if (end) {
+            is_dc = true;
+            blk_start = pos;
+            budget = block_budget(pos, total_bits);
+        }
+        return end;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Single-block parser for the block-parallel decode kernels: the same trajectory function as
+// Parser::step, restricted to one block, delivering coefficients to a sink.
+// Sink::dc(e) / Sink::ac(zigzag_index, e).
 // ------------------------------------------------------------------------------------------------
 template <class Sink>
-__device__ __forceinline__ uint32_t parse_block(BitReader& r, uint32_t max_bits, Sink& sink) {
+__device__ __forceinline__ void parse_block(const uint8_t* base, uint32_t bitpos, uint32_t total_bits, Sink& sink) {
+    BitReader r;
+    r.init(base, bitpos);
+    const uint32_t max_bits = block_budget(bitpos, total_bits);
     r.refill();
     uint32_t t = r.top();
-    int size = (int)(t >> 28);
+    uint32_t size = t >> 28;
     int e = 0;
-    if (size) e = vli_extend((t << 4) >> (32 - size), size);
-    r.skip(4 + size);
-    uint32_t used = 4u + (uint32_t)size;
+    if (size) e = vli_extend((t << 4) >> (32u - size), (int)size);
+    r.skip((int)(4u + size));
+    uint32_t used = 4u + size;
     sink.dc(e);
     uint32_t idx = 1;
     while (used < max_bits) {
         r.refill();
         t = r.top();
-        int run = (int)(t >> 28);
-        size = (int)((t >> 24) & 15u);
-        r.skip(8 + size);
-        used += 8u + (uint32_t)size;
+        const uint32_t run = t >> 28;
+        size = (t >> 24) & 15u;
+        r.skip((int)(8u + size));
+        used += 8u + size;
         if (size == 0) {
-            if (run != 15) break;             // END
+            if (run != 15u) break;            // END
             idx = (idx + 16u) & 255u;         // ZRL
             continue;
         }
-        e = vli_extend((t << 8) >> (32 - size), size);
-        idx = (idx + (uint32_t)run) & 255u;
+        e = vli_extend((t << 8) >> (32u - size), (int)size);
+        idx = (idx + run) & 255u;
         if (idx < 64u) sink.ac(idx, e);
         if (idx >= 63u) break;
         idx++;
     }
-    return used;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -159,9 +226,41 @@ __device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xFFFF
 __device__ __forceinline__ int hi16(uint32_t w) { return (int)w >> 16; }
 __device__ __forceinline__ uint32_t clamp255(int v) { return (uint32_t)min(max(v, 0), 255); }  // NORMALIZE, idct.c:20
 
+// Column occupancy of a block held as 8 rows of packed int16: bit c of `ac` is set when column c has a
+// non-zero coefficient in rows 1..7, bit c of `any` when it has one in any row.
+__device__ __forceinline__ void block_masks(const uint4 (&rows)[8], uint32_t& ac, uint32_t& any) {
+    uint32_t a[4] = {rows[1].x, rows[1].y, rows[1].z, rows[1].w};
+#pragma unroll
+    for (int r = 2; r < 8; r++) { a[0] |= rows[r].x; a[1] |= rows[r].y; a[2] |= rows[r].z; a[3] |= rows[r].w; }
+    const uint32_t n[4] = {a[0] | rows[0].x, a[1] | rows[0].y, a[2] | rows[0].z, a[3] | rows[0].w};
+    ac = any = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        ac |= ((a[j] & 0xFFFFu) ? 1u : 0u) << (2 * j) | ((a[j] >> 16) ? 1u : 0u) << (2 * j + 1);
+        any |= ((n[j] & 0xFFFFu) ? 1u : 0u) << (2 * j) | ((n[j] >> 16) ? 1u : 0u) << (2 * j + 1);
+    }
+}
+
 // Full 8x8 IDCT of one block held as 8 rows of packed int16 (uint4 = one 16-byte row).
 // Output: 16 words, word 2r / 2r+1 = pixels 0-3 / 4-7 of row r (little-endian bytes).
-__device__ __forceinline__ void idct_block(const uint4 (&rows)[8], uint32_t (&out)[16]) {
+//
+// acmask / anymask are WARP-UNIFORM supersets of block_masks() over the warp's 32 blocks, so every
+// branch below is divergence-free.  They only select bit-exact shortcuts of the reference arithmetic:
+//   * a column whose rows 1..7 are zero: every pass-1 output is DESCALE(in0 << 13, 11) == in0 << 2
+//     (the low 11 bits of in0 << 13 are zero, so the rounding term never carries) -- idct.c:55-63,99-106;
+//   * an all-zero column gives an all-zero workspace column;
+//   * workspace columns 4..7 all zero: pass 2 with those inputs as literal zeros (same expression tree);
+//   * only column 0 non-zero and no AC in it (DC-only blocks): pass 2 is DESCALE(ws << 13, 18) ==
+//     (ws + 16) >> 5 with ws = dc << 2 -- idct.c:123-180.
+// Pass 0xFF / 0xFF to disable every shortcut.
+__device__ __forceinline__ void idct_block(const uint4 (&rows)[8], uint32_t acmask, uint32_t anymask,
+                                           uint32_t (&out)[16]) {
+    if (((anymask & 0xFEu) | (acmask & 1u)) == 0) {
+        const uint32_t v = clamp255(((lo16(rows[0].x) << 2) + 16) >> 5) * 0x01010101u;
+#pragma unroll
+        for (int k = 0; k < 16; k++) out[k] = v;
+        return;
+    }
     int ws[8][8];
     // Pass 1: columns (idct.c:41-109).  Column c takes element c of every row.
 #pragma unroll
@@ -172,20 +271,30 @@ __device__ __forceinline__ void idct_block(const uint4 (&rows)[8], uint32_t (&ou
             uint32_t w = (c >> 1) == 0 ? rows[r].x : (c >> 1) == 1 ? rows[r].y : (c >> 1) == 2 ? rows[r].z : rows[r].w;
             in[r] = (c & 1) ? hi16(w) : lo16(w);
         }
-        int o[8];
-        idct8<11>(in[0], in[1], in[2], in[3], in[4], in[5], in[6], in[7], o);
+        if (acmask & (1u << c)) {
+            int o[8];
+            idct8<11>(in[0], in[1], in[2], in[3], in[4], in[5], in[6], in[7], o);
 #pragma unroll
-        for (int r = 0; r < 8; r++) ws[r][c] = o[r];
+            for (int r = 0; r < 8; r++) ws[r][c] = o[r];
+        } else {
+            const int v = (anymask & (1u << c)) ? (int)((unsigned)in[0] << 2) : 0;
+#pragma unroll
+            for (int r = 0; r < 8; r++) ws[r][c] = v;
+        }
     }
     // Pass 2: rows (idct.c:116-180), clamp to 0..255, no level shift.
+    const bool low_half_only = (anymask & 0xF0u) == 0;
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         int o[8];
-        idct8<18>(ws[r][0], ws[r][1], ws[r][2], ws[r][3], ws[r][4], ws[r][5], ws[r][6], ws[r][7], o);
+        if (low_half_only) idct8<18>(ws[r][0], ws[r][1], ws[r][2], ws[r][3], 0, 0, 0, 0, o);
+        else idct8<18>(ws[r][0], ws[r][1], ws[r][2], ws[r][3], ws[r][4], ws[r][5], ws[r][6], ws[r][7], o);
         out[2 * r] = clamp255(o[0]) | (clamp255(o[1]) << 8) | (clamp255(o[2]) << 16) | (clamp255(o[3]) << 24);
         out[2 * r + 1] = clamp255(o[4]) | (clamp255(o[5]) << 8) | (clamp255(o[6]) << 16) | (clamp255(o[7]) << 24);
     }
 }
+
+__device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_sync(0xFFFFFFFFu, v); }
 
 // YCbCr -> packed BGRA word: LIB/decoder/ycbcr_to_rgb.c:31-46.  NORMALIZE_RGB (:19): negative -> 0,
 // else >> 14 then cap at 255.  Word = B | G<<8 | R<<16 | A(0)<<24 (rgb_pixel_t, mjpeg423_types.h:56-61).
@@ -207,6 +316,18 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
                  "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
+}
+
+// One block row (8 pixels) of Y/Cb/Cr packed samples -> 8 BGRA words, stored as one 32-byte sector.
+__device__ __forceinline__ void colour_row_store(uint32_t y0, uint32_t y1, uint32_t cb0, uint32_t cb1, uint32_t cr0,
+                                                 uint32_t cr1, uint8_t* dst) {
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        v[k] = ycc_to_bgra((y0 >> (8 * k)) & 255u, (cb0 >> (8 * k)) & 255u, (cr0 >> (8 * k)) & 255u);
+        v[4 + k] = ycc_to_bgra((y1 >> (8 * k)) & 255u, (cb1 >> (8 * k)) & 255u, (cr1 >> (8 * k)) & 255u);
+    }
+    st_global_v8(dst, v);
 }
 
 }  // namespace mj

@@ -1,6 +1,6 @@
-// entropy.cu -- batched, segment-parallel "lossless" decode + dequantise (sm_100a).
+// entropy.cu -- batched, segment-parallel "lossless" decode (sm_100a): synchronisation, chain, block index.
 //
-// Replaces lossless_decode(), LIB/decoder/lossless_decode.c:60-135 (LIB =
+// Replaces the serial walk of lossless_decode(), LIB/decoder/lossless_decode.c:60-135 (LIB =
 // /root/reference/core0/software/common/libs/mjpeg423), for MANY plane streams at once and, inside a
 // stream, for many fixed-size bitstream segments in parallel.  The code has no markers or restart
 // intervals, so segment entry points are found by self-synchronisation:
@@ -10,52 +10,45 @@
 //                    CP_BITS boundary, blocks and DC sum so far).  The predecessor's speculative exit
 //                    is then taken as the segment's entry and parsed only until it MERGES with the
 //                    recorded trajectory (same bit position at a block start => identical future).
-//   k_entropy_chain  one CTA per stream: re-parses the few segments whose entry differs from the
+//                    A second in-CTA round re-merges the segments whose predecessor's exit moved.
+//   k_entropy_chain  one CTA per stream: re-parses the few segments whose entry still differs from the
 //                    predecessor's resolved exit until the chain entry[i] == exit[i-1] holds from
 //                    entry[0] = 0 (correctness never rests on self-synchronisation, only speed does),
 //                    then exclusive-scans block counts and DC sums (mod 2^16) to
 //                    give every segment its first block index and DC predictor.
-//   k_entropy_write  one thread per segment decodes its blocks from the now exact state, dequantises
-//                    and scatters int16 coefficients in zig-zag -> natural order into a plane the CTA
-//                    has just zero-filled with coalesced 128-bit stores (the memset at :77-78).
+//   k_entropy_index  one thread per segment walks its blocks from the now exact state and writes, per
+//                    block, the bit position of its DC symbol and the absolute DC level: the index the
+//                    block-parallel decode kernels (decode.cu) start from.
 //
-// All three parse with the same parse_block() (common.cuh), so they follow one trajectory function.
+// Every pass advances with Parser::step() (common.cuh): one flat loop, one symbol per iteration per
+// lane, DC/AC and block-end handling predicated, so the lanes of a warp stay converged.
 #include "common.cuh"
 #include "runtime.h"
 
 namespace mj {
 
-__constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
-                                     12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
-                                     35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
-                                     58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-
-struct ParseSink {          // parse-only: accumulate the DC delta (mod 2^16 is taken by the caller)
-    int dcsum = 0;
-    __device__ __forceinline__ void dc(int e) { dcsum += e; }
-    __device__ __forceinline__ void ac(uint32_t, int) {}
-};
-
-__device__ __forceinline__ uint32_t block_budget(uint32_t pos, uint32_t total_bits) {
-    return min(RUNAWAY_BITS, total_bits - pos);
-}
-
-// Parse segment `seg` from block start `entry` to the first block start at or after the segment end
-// (or the end of the stream).  Returns exit; cnt / dc receive the blocks started and their DC sum.
+// Parse from block start `entry` to the first block start at or after seg_end (or the end of the
+// stream).  Returns the exit position; cnt / dc receive the blocks started and their DC sum mod 2^16.
 __device__ __forceinline__ uint32_t parse_segment(const uint8_t* base, uint32_t entry, uint32_t seg_end,
                                                   uint32_t total_bits, uint32_t& cnt, uint32_t& dc) {
-    uint32_t pos = entry;
-    ParseSink sink;
     cnt = 0;
+    int dcsum = 0;
+    uint32_t pos = entry;
     if (pos < seg_end && pos + MIN_BLOCK_BITS <= total_bits) {
-        BitReader r;
-        r.init(base, pos);
-        do {
-            pos += parse_block(r, block_budget(pos, total_bits), sink);
-            cnt++;
-        } while (pos < seg_end && pos + MIN_BLOCK_BITS <= total_bits);
+        Parser ps;
+        ps.start(base, entry, total_bits);
+        for (;;) {
+            int e;
+            const bool end = ps.step(total_bits, e);
+            dcsum += e;
+            if (end) {
+                cnt++;
+                if (ps.pos >= seg_end || ps.pos + MIN_BLOCK_BITS > total_bits) break;
+            }
+        }
+        pos = ps.pos;
     }
-    dc = (uint32_t)sink.dcsum & 0xFFFFu;
+    dc = (uint32_t)dcsum & 0xFFFFu;
     return pos;
 }
 
@@ -63,12 +56,66 @@ __device__ __forceinline__ uint32_t parse_segment(const uint8_t* base, uint32_t 
 // Speculative parse + merge.  A tile owns ENT_TPB-1 segments; thread 0 parses the segment BEFORE the
 // tile (halo) so that thread 1 has a predecessor exit without any inter-CTA dependency.
 // ------------------------------------------------------------------------------------------------
+struct Resolved { uint32_t exit_pos, cnt, dc; };
+
+// Resolve segment [seg_start, seg_end) for true entry E against the recorded speculative trajectory.
+__device__ __forceinline__ Resolved resolve_by_merge(const uint8_t* base, uint32_t E, uint32_t seg_start,
+                                                     uint32_t seg_end, uint32_t total_bits,
+                                                     const uint32_t (*s_pos)[ENT_TPB], const uint32_t (*s_cd)[ENT_TPB],
+                                                     int t) {
+    const uint32_t spec_exit = s_pos[NCP - 1][t], spec_cd = s_cd[NCP - 1][t];
+    Resolved rs{E, 0, 0};
+    if (E >= seg_end) return rs;                         // a block spans the whole segment: it owns nothing
+    if (E == seg_start) {                                // speculation started on the true entry
+        rs.exit_pos = spec_exit; rs.cnt = spec_cd & 0xFFFFu; rs.dc = spec_cd >> 16;
+        return rs;
+    }
+    if (E + MIN_BLOCK_BITS > total_bits) return rs;
+    if (E >= seg_start + CP_BITS) {                      // E itself may be a recorded block start
+        const int j = (int)((E - seg_start) / CP_BITS) - 1;
+        if (s_pos[j][t] == E) {
+            const uint32_t at = s_cd[j][t];
+            rs.exit_pos = spec_exit;
+            rs.cnt = (spec_cd & 0xFFFFu) - (at & 0xFFFFu);
+            rs.dc = ((spec_cd >> 16) - (at >> 16)) & 0xFFFFu;
+            return rs;
+        }
+    }
+    Parser ps;
+    ps.start(base, E, total_bits);
+    int dcsum = 0;
+    uint32_t cnt = 0;
+    for (;;) {
+        int e;
+        const bool end = ps.step(total_bits, e);
+        dcsum += e;
+        if (!end) continue;
+        cnt++;
+        const uint32_t pos = ps.pos;
+        if (pos >= seg_start + CP_BITS) {
+            const int j = (int)min((uint32_t)NCP, (pos - seg_start) / CP_BITS) - 1;
+            if (s_pos[j][t] == pos) {                    // merged with the speculative trajectory
+                const uint32_t at = s_cd[j][t];
+                cnt += (spec_cd & 0xFFFFu) - (at & 0xFFFFu);
+                dcsum += (int)(spec_cd >> 16) - (int)(at >> 16);
+                rs.exit_pos = spec_exit;
+                break;
+            }
+        }
+        if (pos >= seg_end || pos + MIN_BLOCK_BITS > total_bits) { rs.exit_pos = pos; break; }
+    }
+    rs.cnt = cnt;
+    rs.dc = (uint32_t)dcsum & 0xFFFFu;
+    return rs;
+}
+
 __global__ void __launch_bounds__(ENT_TPB)
 k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
                const TileDesc* __restrict__ tiles, uint32_t* __restrict__ seg_entry,
                uint32_t* __restrict__ seg_exit, uint32_t* __restrict__ seg_cd) {
     __shared__ uint32_t s_pos[NCP][ENT_TPB];   // [j] = first block start >= seg_start + (j+1)*CP_BITS
     __shared__ uint32_t s_cd[NCP][ENT_TPB];    // blocks started before it | DC sum of them << 16
+    __shared__ uint32_t s_rexit[ENT_TPB];      // resolved exits (round 1)
     const int t = threadIdx.x;
     const TileDesc td = tiles[blockIdx.x];
     const StreamDesc sd = streams[td.stream];
@@ -78,65 +125,60 @@ k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
     const uint32_t total_bits = sd.byte_len * 8u;
     const uint32_t seg_start = (uint32_t)seg * SEG_BITS, seg_end = seg_start + SEG_BITS;
 
+    // ---- speculative parse from the segment's first bit --------------------------------------------
     if (valid) {
-        uint32_t pos = seg_start, cnt = 0;
-        ParseSink sink;
-        BitReader r;
-        r.init(base, pos);
         int j = 0;
-        for (;;) {
-            while (j < NCP && pos >= seg_start + (uint32_t)(j + 1) * CP_BITS) {
-                s_pos[j][t] = pos;
-                s_cd[j][t] = cnt | ((uint32_t)sink.dcsum << 16);
-                j++;
+        uint32_t cnt = 0;
+        int dcsum = 0;
+        uint32_t pos = seg_start;
+        if (pos + MIN_BLOCK_BITS <= total_bits) {
+            Parser ps;
+            ps.start(base, seg_start, total_bits);
+            uint32_t next_cp = seg_start + CP_BITS;
+            for (;;) {
+                int e;
+                const bool end = ps.step(total_bits, e);
+                dcsum += e;
+                if (!end) continue;
+                cnt++;
+                pos = ps.pos;
+                if (pos >= next_cp) {
+                    const uint32_t rec = cnt | ((uint32_t)dcsum << 16);
+                    do { s_pos[j][t] = pos; s_cd[j][t] = rec; j++; next_cp += CP_BITS; } while (j < NCP && pos >= next_cp);
+                    if (j == NCP) break;
+                }
+                if (pos + MIN_BLOCK_BITS > total_bits) break;     // end of stream: no further block can start
             }
-            if (j == NCP) break;
-            if (pos + MIN_BLOCK_BITS > total_bits) {       // end of stream: no further block can start
-                for (; j < NCP; j++) { s_pos[j][t] = pos; s_cd[j][t] = cnt | ((uint32_t)sink.dcsum << 16); }
-                break;
-            }
-            pos += parse_block(r, block_budget(pos, total_bits), sink);
-            cnt++;
         }
+        const uint32_t rec = cnt | ((uint32_t)dcsum << 16);
+        for (; j < NCP; j++) { s_pos[j][t] = pos; s_cd[j][t] = rec; }
     }
     __syncthreads();
-    if (!valid || t == 0) return;
 
-    const uint32_t spec_exit = s_pos[NCP - 1][t], spec_cd = s_cd[NCP - 1][t];
-    const uint32_t E = seg == 0 ? 0u : s_pos[NCP - 1][t - 1];
-    uint32_t exit_pos, cnt = 0, dc = 0;
-    if (E >= seg_end) {                 // a block spans the whole segment: it owns nothing
-        exit_pos = E;
-    } else if (E == seg_start) {        // speculation started on the true entry
-        exit_pos = spec_exit; cnt = spec_cd & 0xFFFFu; dc = spec_cd >> 16;
-    } else {
-        uint32_t pos = E;
-        ParseSink sink;
-        BitReader r;
-        r.init(base, pos);
-        for (;;) {
-            if (pos >= seg_start + CP_BITS) {
-                int j = (int)min((uint32_t)NCP, (pos - seg_start) / CP_BITS) - 1;
-                if (s_pos[j][t] == pos) {                  // merged with the speculative trajectory
-                    uint32_t at = s_cd[j][t];
-                    cnt += (spec_cd & 0xFFFFu) - (at & 0xFFFFu);
-                    sink.dcsum += (int)(spec_cd >> 16) - (int)(at >> 16);
-                    pos = spec_exit;
-                    break;
-                }
-                if (pos >= seg_end) break;
-            }
-            if (pos + MIN_BLOCK_BITS > total_bits) break;
-            pos += parse_block(r, block_budget(pos, total_bits), sink);
-            cnt++;
-        }
-        exit_pos = pos;
-        dc = (uint32_t)sink.dcsum & 0xFFFFu;
+    // ---- round 1: entry = predecessor's speculative exit -------------------------------------------------
+    const bool own = valid && t >= 1;
+    uint32_t E = 0;
+    Resolved rs{0, 0, 0};
+    if (own) {
+        E = seg == 0 ? 0u : s_pos[NCP - 1][t - 1];
+        rs = resolve_by_merge(base, E, seg_start, seg_end, total_bits, s_pos, s_cd, t);
     }
-    const uint32_t g = sd.seg_base + (uint32_t)seg;
-    seg_entry[g] = E;
-    seg_exit[g] = exit_pos;
-    seg_cd[g] = (cnt & 0xFFFFu) | (dc << 16);
+    s_rexit[t] = own ? rs.exit_pos : (valid ? s_pos[NCP - 1][t] : 0u);   // the halo keeps its speculative exit
+    __syncthreads();
+    // ---- round 2: re-merge where the predecessor's resolved exit differs from its speculative one ----------
+    if (own && seg != 0) {
+        const uint32_t E2 = s_rexit[t - 1];
+        if (E2 != E) {
+            E = E2;
+            rs = resolve_by_merge(base, E, seg_start, seg_end, total_bits, s_pos, s_cd, t);
+        }
+    }
+    if (own) {
+        const uint32_t g = sd.seg_base + (uint32_t)seg;
+        seg_entry[g] = E;
+        seg_exit[g] = rs.exit_pos;
+        seg_cd[g] = (rs.cnt & 0xFFFFu) | (rs.dc << 16);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -208,79 +250,45 @@ k_entropy_chain(const uint8_t* __restrict__ payload, const StreamDesc* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// Coefficient write.  quant: 2 tables x 64 int16, natural order (LIB/common/tables.c:13-32 by default).
+// Block index: per block, the bit position of its DC symbol and its absolute DC level
+// (`cur` of LIB/decoder/lossless_decode.c:73,94 -- the running sum of DC deltas, int16).
 // ------------------------------------------------------------------------------------------------
-template <bool PFRAME>
-struct WriteSink {
-    int16_t* out;               // current block, natural order
-    const uint32_t* zq;         // smem: natural index | quant << 16, by zig-zag position
-    int cur;                    // I frames: running DC (LIB/decoder/lossless_decode.c:73,94)
-    __device__ __forceinline__ void dc(int e) {
-        int q0 = (int)(zq[0] >> 16);
-        if (PFRAME) out[0] = (int16_t)(out[0] + e * q0);          // :91
-        else { cur += e; out[0] = (int16_t)((int)(int16_t)cur * q0); }   // :94-95
-    }
-    __device__ __forceinline__ void ac(uint32_t idx, int e) {
-        uint32_t z = zq[idx];
-        int n = (int)(z & 0xFFFFu), q = (int)(z >> 16);
-        if (PFRAME) out[n] = (int16_t)(out[n] + e * q);           // :122
-        else out[n] = (int16_t)(e * q);                           // :125
-    }
-};
-
 __global__ void __launch_bounds__(ENT_TPB)
-k_entropy_write(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
+k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
                 const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ seg_entry,
                 const uint32_t* __restrict__ seg_cd, const uint32_t* __restrict__ seg_first,
-                const int16_t* __restrict__ quant, int16_t* __restrict__ coef) {
-    __shared__ uint32_t s_zq[64];
-    __shared__ uint32_t s_range[2];
+                uint32_t* __restrict__ blk_pos, int16_t* __restrict__ blk_dc) {
     const int t = threadIdx.x;
     const TileDesc td = tiles[blockIdx.x];
     const StreamDesc sd = streams[td.stream];
     const uint32_t seg = td.seg0 + (uint32_t)t;
-    const bool valid = seg < sd.nseg;
+    if (seg >= sd.nseg) return;
     const uint8_t* base = payload + sd.byte_off;
     const uint32_t total_bits = sd.byte_len * 8u;
-    if (t < 64) {
-        uint32_t n = c_zigzag[t];
-        s_zq[t] = n | ((uint32_t)(uint16_t)quant[sd.quant_id * 64 + n] << 16);
+    const uint32_t g = sd.seg_base + seg;
+    const uint32_t first = seg_first[g];
+    const uint32_t cd = seg_cd[g];
+    uint32_t cnt = cd & 0xFFFFu;
+    cnt = first >= sd.nb ? 0u : min(cnt, sd.nb - first);          // trailing pad bits can look like blocks
+    uint32_t* bp = blk_pos + sd.block_base + first;
+    int16_t* bd = blk_dc + sd.block_base + first;
+    if (cnt) {
+        Parser ps;
+        ps.start(base, seg_entry[g], total_bits);
+        int cur = (int)(cd >> 16);
+        uint32_t k = 0;
+        for (;;) {
+            const bool was_dc = ps.is_dc;
+            const uint32_t at = ps.pos;
+            int e;
+            const bool end = ps.step(total_bits, e);
+            if (was_dc) { cur += e; bp[k] = at; bd[k] = (int16_t)cur; }
+            if (end && ++k == cnt) break;
+        }
     }
-    uint32_t E = 0, first = 0, cnt = 0, dc0 = 0;
-    if (valid) {
-        const uint32_t g = sd.seg_base + seg;
-        E = seg_entry[g];
-        first = seg_first[g];
-        uint32_t cd = seg_cd[g];
-        cnt = cd & 0xFFFFu;
-        dc0 = cd >> 16;
-        if (first >= sd.nb) cnt = 0;
-        else cnt = min(cnt, sd.nb - first);       // trailing pad bits can look like blocks
-    }
-    int16_t* plane = coef + (size_t)sd.block_base * 64;
-    const bool last_tile = td.seg0 + ENT_TPB >= sd.nseg;
-    if (!sd.ptype) {
-        // Zero-fill the tile's contiguous block range (the memset of :77-78), coalesced.
-        if (t == 0) s_range[0] = min(first, sd.nb);
-        if (valid && (seg + 1 == sd.nseg || t == ENT_TPB - 1)) s_range[1] = last_tile ? sd.nb : first + cnt;
-        __syncthreads();
-        uint4* z = reinterpret_cast<uint4*>(plane + (size_t)s_range[0] * 64);
-        const uint32_t nvec = (s_range[1] - s_range[0]) * 8u;     // 8 x 16 B per block
-        for (uint32_t i = t; i < nvec; i += ENT_TPB) z[i] = make_uint4(0, 0, 0, 0);
-    }
-    __syncthreads();
-    if (cnt == 0) return;
-
-    BitReader r;
-    r.init(base, E);
-    uint32_t pos = E;
-    if (sd.ptype) {
-        WriteSink<true> sink{plane + (size_t)first * 64, s_zq, 0};
-        for (uint32_t k = 0; k < cnt; k++, sink.out += 64) pos += parse_block(r, block_budget(pos, total_bits), sink);
-    } else {
-        WriteSink<false> sink{plane + (size_t)first * 64, s_zq, (int)dc0};
-        for (uint32_t k = 0; k < cnt; k++, sink.out += 64) pos += parse_block(r, block_budget(pos, total_bits), sink);
-    }
+    // A stream that ends early leaves the remaining blocks empty (zero coefficients).
+    if (seg + 1 == sd.nseg)
+        for (uint32_t b = first + cnt; b < sd.nb; b++) { blk_pos[sd.block_base + b] = NO_BLOCK; blk_dc[sd.block_base + b] = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -299,10 +307,10 @@ cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s) {
                                                       j.d_stream_blocks + j.stream_lo, j.d_fixups);
     return cudaGetLastError();
 }
-cudaError_t launch_entropy_write(const EntropyJob& j, const int16_t* d_quant, int16_t* d_coef, cudaStream_t s) {
+cudaError_t launch_entropy_index(const EntropyJob& j, cudaStream_t s) {
     if (j.n_write_tiles == 0) return cudaSuccess;
-    k_entropy_write<<<j.n_write_tiles, ENT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_write_tiles, j.d_seg_entry,
-                                                        j.d_seg_cd, j.d_seg_first, d_quant, d_coef);
+    k_entropy_index<<<j.n_write_tiles, ENT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_write_tiles, j.d_seg_entry,
+                                                        j.d_seg_cd, j.d_seg_first, j.d_blk_pos, j.d_blk_dc);
     return cudaGetLastError();
 }
 

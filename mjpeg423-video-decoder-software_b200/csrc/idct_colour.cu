@@ -57,26 +57,20 @@ k_idct(const int16_t* __restrict__ coef, uint8_t* __restrict__ samples, size_t n
     stage_tile(tile, coef + b0 * 64, nblk, t);
     cp_async_wait_all();
     __syncthreads();
-    if (t >= nblk) return;
+    const bool live = t < nblk;
     uint4 rows[8];
-    load_block_rows(tile, t, rows);
+    uint32_t ac = 0, any = 0;
+    if (live) { load_block_rows(tile, t, rows); block_masks(rows, ac, any); }
+    else {
+#pragma unroll
+        for (int r = 0; r < 8; r++) rows[r] = make_uint4(0, 0, 0, 0);
+    }
     uint32_t px[16];
-    idct_block(rows, px);
+    idct_block(rows, warp_or(ac), warp_or(any), px);
+    if (!live) return;
     uint4* dst = reinterpret_cast<uint4*>(samples + (b0 + t) * 64);
 #pragma unroll
     for (int k = 0; k < 4; k++) dst[k] = make_uint4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
-}
-
-// One block row (8 pixels) of Y/Cb/Cr packed samples -> 8 BGRA words, stored as one 32-byte sector.
-__device__ __forceinline__ void colour_row_store(uint32_t y0, uint32_t y1, uint32_t cb0, uint32_t cb1, uint32_t cr0,
-                                                 uint32_t cr1, uint8_t* dst) {
-    uint32_t v[8];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        v[k] = ycc_to_bgra((y0 >> (8 * k)) & 255u, (cb0 >> (8 * k)) & 255u, (cr0 >> (8 * k)) & 255u);
-        v[4 + k] = ycc_to_bgra((y1 >> (8 * k)) & 255u, (cb1 >> (8 * k)) & 255u, (cr1 >> (8 * k)) & 255u);
-    }
-    st_global_v8(dst, v);
 }
 
 // ---- ycbcr_to_rgb(): sample planes (frame-major, Y|Cb|Cr, block-major) -> BGRA raster ---------------
@@ -99,7 +93,7 @@ k_colour(const uint8_t* __restrict__ samples, uint8_t* __restrict__ out, uint32_
 }
 
 // ---- fused IDCT + colour: coefficient planes (frame-major, Y|Cb|Cr) -> BGRA raster ------------------
-__global__ void __launch_bounds__(IDCT_TPB)
+__global__ void __launch_bounds__(IDCT_TPB, 4)
 k_idct_colour(const int16_t* __restrict__ coef, uint8_t* __restrict__ out, uint32_t nb, uint32_t wb, uint32_t W) {
     extern __shared__ __align__(128) uint8_t smem[];          // 3 x TILE_BYTES
     const int t = threadIdx.x;
@@ -111,20 +105,25 @@ k_idct_colour(const int16_t* __restrict__ coef, uint8_t* __restrict__ out, uint3
     for (int p = 0; p < 3; p++) stage_tile(smem + p * TILE_BYTES, fc + ((size_t)p * nb + b0) * 64, nblk, t);
     cp_async_wait_all();
     __syncthreads();
-    if (t >= nblk) return;
-    uint4 rows[8];
-    uint32_t y[16], cb[16], cr[16];
-    load_block_rows(smem, t, rows);
-    idct_block(rows, y);
-    load_block_rows(smem + TILE_BYTES, t, rows);
-    idct_block(rows, cb);
-    load_block_rows(smem + 2 * TILE_BYTES, t, rows);
-    idct_block(rows, cr);
+    const bool live = t < nblk;
+    uint32_t px[3][16];
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+        uint4 rows[8];
+        uint32_t ac = 0, any = 0;
+        if (live) { load_block_rows(smem + p * TILE_BYTES, t, rows); block_masks(rows, ac, any); }
+        else {
+#pragma unroll
+            for (int r = 0; r < 8; r++) rows[r] = make_uint4(0, 0, 0, 0);
+        }
+        idct_block(rows, warp_or(ac), warp_or(any), px[p]);
+    }
+    if (!live) return;
     const uint32_t b = b0 + (uint32_t)t;
     uint8_t* dst = out + ((size_t)f * nb * 64 + ((size_t)(b / wb) * 8 * W + (size_t)(b % wb) * 8)) * 4;
 #pragma unroll
     for (int r = 0; r < 8; r++)
-        colour_row_store(y[2 * r], y[2 * r + 1], cb[2 * r], cb[2 * r + 1], cr[2 * r], cr[2 * r + 1],
+        colour_row_store(px[0][2 * r], px[0][2 * r + 1], px[1][2 * r], px[1][2 * r + 1], px[2][2 * r], px[2][2 * r + 1],
                          dst + (size_t)r * W * 4);
 }
 

@@ -77,8 +77,7 @@ int build_plan(const MpgIndex& idx, uint32_t first, uint32_t n, Plan& plan) {
     }
     if ((uint64_t)n * 3 * plan.nb >= 0xFFFFFFFFull) { set_error("too many blocks in one plan"); return MJPEG423_E_ARG; }
     plan.frames.assign(idx.frames.begin() + first, idx.frames.begin() + first + n);
-    for (const FrameRec& r : plan.frames)
-        if (r.type != 0) { set_error("P frames are not supported by the batched path yet"); return MJPEG423_E_PFRAME; }
+    for (const FrameRec& r : plan.frames) plan.n_pframes += r.type != 0;
     plan.payload_off = plan.frames.front().off;
     plan.payload_len = plan.frames.back().off + plan.frames.back().size - plan.payload_off;
     plan.streams.reserve((size_t)n * 3);
@@ -98,6 +97,7 @@ int build_plan(const MpgIndex& idx, uint32_t first, uint32_t n, Plan& plan) {
             sd.seg_base = seg_base;
             sd.nseg = std::max<uint32_t>(1, (lens[p] + SEG_BYTES - 1) / SEG_BYTES);
             sd.block_base = (f * 3 + p) * plan.nb;
+            sd.prev_base = r.type ? sd.block_base - 3 * plan.nb : sd.block_base;   // frame 0 is an I frame
             sd.quant_id = p ? 1 : 0; sd.ptype = (uint16_t)r.type;
             const uint32_t sidx = (uint32_t)plan.streams.size();
             for (uint32_t s0 = 0; s0 < sd.nseg; s0 += ENT_TPB - 1) plan.sync_tiles.push_back({sidx, s0});
@@ -111,6 +111,37 @@ int build_plan(const MpgIndex& idx, uint32_t first, uint32_t n, Plan& plan) {
     plan.f_write0[n] = (uint32_t)plan.write_tiles.size();
     plan.f_seg0[n] = seg_base;
     return MJPEG423_OK;
+}
+
+// Cut the plan into chunks of about K frames that start on I frames, and order each chunk's streams by
+// GOP depth (see Chunk in runtime.h).  For intra-only plans `ids` is simply 0, 1, 2, ...
+void make_chunks(const Plan& plan, uint32_t K, std::vector<Chunk>& chunks, std::vector<uint32_t>& ids) {
+    chunks.clear(); ids.clear();
+    ids.reserve((size_t)plan.n * 3);
+    K = std::max<uint32_t>(1, K);
+    uint32_t f = 0;
+    while (f < plan.n) {
+        Chunk ch;
+        ch.f0 = f;
+        uint32_t e = (uint32_t)std::min<uint64_t>(plan.n, (uint64_t)f + K);
+        while (e < plan.n && plan.frames[e].type != 0) e++;          // never split a GOP
+        ch.f1 = e;
+        ch.ids_off = (uint32_t)ids.size();
+        std::vector<uint32_t> depth(e - f);
+        uint32_t maxd = 0;
+        for (uint32_t k = f; k < e; k++) {
+            depth[k - f] = plan.frames[k].type ? depth[k - f - 1] + 1 : 0;
+            maxd = std::max(maxd, depth[k - f]);
+        }
+        for (uint32_t l = 0; l <= maxd; l++) {
+            ch.level_off.push_back((uint32_t)ids.size() - ch.ids_off);
+            for (uint32_t k = f; k < e; k++)
+                if (depth[k - f] == l) for (uint32_t p = 0; p < 3; p++) ids.push_back(k * 3 + p);
+        }
+        ch.level_off.push_back((uint32_t)ids.size() - ch.ids_off);
+        chunks.push_back(std::move(ch));
+        f = e;
+    }
 }
 
 }  // namespace mj
@@ -184,8 +215,9 @@ extern "C" void mjpeg423_b200_destroy(mjpeg423_b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&c->payload, &c->tables, &c->segs, &c->coef[0], &c->coef[1], &c->samples, &c->stream_blocks,
-                      &c->misc, &c->in_ring[0], &c->in_ring[1], &c->out_ring[0], &c->out_ring[1]})
+    for (DevBuf* b : {&c->payload, &c->tables, &c->segs, &c->coef[0], &c->coef[1], &c->blkidx[0], &c->blkidx[1],
+                      &c->samples, &c->stream_blocks, &c->misc, &c->ids, &c->in_ring[0], &c->in_ring[1], &c->out_ring[0],
+                      &c->out_ring[1]})
         b->release();
     for (int i = 0; i < 2; i++) if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
     if (c->d_quant) cudaFree(c->d_quant);
@@ -198,7 +230,10 @@ extern "C" int mjpeg423_b200_set_option(mjpeg423_b200_ctx* c, int option, int64_
     if (!c) return MJPEG423_E_ARG;
     switch (option) {
         case MJPEG423_OPT_PROFILE: c->profile = value != 0; return MJPEG423_OK;
-        case MJPEG423_OPT_STAGED: c->staged = value != 0; return MJPEG423_OK;
+        case MJPEG423_OPT_STAGED:
+            if (value < 0 || value > 2) { set_error("STAGED must be 0, 1 or 2"); return MJPEG423_E_ARG; }
+            c->staged = (int)value;
+            return MJPEG423_OK;
         case MJPEG423_OPT_CHUNK_FRAMES: c->chunk_frames = value < 0 ? 0 : (uint32_t)value; return MJPEG423_OK;
         case MJPEG423_OPT_VALIDATE: c->validate = value != 0; return MJPEG423_OK;
     }
@@ -235,36 +270,7 @@ struct Tables {           // device addresses inside ctx->tables / ctx->segs
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// Lays the plan's tables out in ctx->tables (uploaded) and ctx->segs (device scratch).
-int upload_tables(mjpeg423_b200_ctx* c, const Plan& plan, Tables& t, cudaStream_t s) {
-    const size_t b_streams = align256(plan.streams.size() * sizeof(StreamDesc));
-    const size_t b_sync = align256(plan.sync_tiles.size() * sizeof(TileDesc));
-    const size_t b_write = align256(plan.write_tiles.size() * sizeof(TileDesc));
-    int rc = c->tables.reserve(b_streams + b_sync + b_write + 256);
-    if (rc) return rc;
-    uint8_t* base = c->tables.as<uint8_t>();
-    t.streams = reinterpret_cast<StreamDesc*>(base);
-    t.sync_tiles = reinterpret_cast<TileDesc*>(base + b_streams);
-    t.write_tiles = reinterpret_cast<TileDesc*>(base + b_streams + b_sync);
-    CU(cudaMemcpyAsync(t.streams, plan.streams.data(), plan.streams.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(t.sync_tiles, plan.sync_tiles.data(), plan.sync_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(t.write_tiles, plan.write_tiles.data(), plan.write_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
-    const size_t nseg = plan.f_seg0.empty() ? 0 : plan.f_seg0.back();
-    const size_t b_seg = align256(nseg * 4);
-    const size_t b_sb = align256(plan.streams.size() * 4);
-    rc = c->segs.reserve(4 * b_seg + b_sb + 256);
-    if (rc) return rc;
-    uint8_t* sb = c->segs.as<uint8_t>();
-    t.seg_entry = reinterpret_cast<uint32_t*>(sb);
-    t.seg_exit = reinterpret_cast<uint32_t*>(sb + b_seg);
-    t.seg_cd = reinterpret_cast<uint32_t*>(sb + 2 * b_seg);
-    t.seg_first = reinterpret_cast<uint32_t*>(sb + 3 * b_seg);
-    t.stream_blocks = reinterpret_cast<uint32_t*>(sb + 4 * b_seg);
-    t.fixups = reinterpret_cast<unsigned long long*>(sb + 4 * b_seg + b_sb);
-    return MJPEG423_OK;
-}
-
-Tables tables_of(mjpeg423_b200_ctx* c, const Plan& plan) {   // recompute the layout of upload_tables
+Tables tables_of(mjpeg423_b200_ctx* c, const Plan& plan) {
     Tables t;
     const size_t b_streams = align256(plan.streams.size() * sizeof(StreamDesc));
     const size_t b_sync = align256(plan.sync_tiles.size() * sizeof(TileDesc));
@@ -284,13 +290,67 @@ Tables tables_of(mjpeg423_b200_ctx* c, const Plan& plan) {   // recompute the la
     return t;
 }
 
+// Lays the plan's tables out in ctx->tables (uploaded) and ctx->segs (device scratch).
+int upload_tables(mjpeg423_b200_ctx* c, const Plan& plan, Tables& t, cudaStream_t s) {
+    const size_t b_streams = align256(plan.streams.size() * sizeof(StreamDesc));
+    const size_t b_sync = align256(plan.sync_tiles.size() * sizeof(TileDesc));
+    const size_t b_write = align256(plan.write_tiles.size() * sizeof(TileDesc));
+    int rc = c->tables.reserve(b_streams + b_sync + b_write + 256);
+    if (rc) return rc;
+    const size_t nseg = plan.f_seg0.empty() ? 0 : plan.f_seg0.back();
+    rc = c->segs.reserve(4 * align256(nseg * 4) + align256(plan.streams.size() * 4) + 256);
+    if (rc) return rc;
+    t = tables_of(c, plan);
+    CU(cudaMemcpyAsync(t.streams, plan.streams.data(), plan.streams.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(t.sync_tiles, plan.sync_tiles.data(), plan.sync_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(t.write_tiles, plan.write_tiles.data(), plan.write_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
+    c->chunk_K = 0;      // chunk table must be rebuilt for this plan
+    return MJPEG423_OK;
+}
+
+// (Re)build the chunk table for chunk size K and upload the level-ordered stream id list.
+int prepare_chunks(mjpeg423_b200_ctx* c, const Plan& plan, uint32_t K, cudaStream_t s) {
+    if (c->chunk_K == K && !c->chunks.empty()) return MJPEG423_OK;
+    std::vector<uint32_t> ids;
+    make_chunks(plan, K, c->chunks, ids);
+    int rc = c->ids.reserve(ids.size() * 4 + 4);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->ids.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));          // `ids` is a local
+    c->chunk_K = K;
+    return MJPEG423_OK;
+}
+
+uint32_t max_chunk_frames(const std::vector<Chunk>& chunks) {
+    uint32_t m = 0;
+    for (const Chunk& ch : chunks) m = std::max(m, ch.f1 - ch.f0);
+    return m;
+}
+
 uint32_t auto_chunk(const Plan& plan, uint64_t target_bytes, uint64_t bytes_per_frame) {
     uint64_t k = target_bytes / std::max<uint64_t>(1, bytes_per_frame);
     k = std::max<uint64_t>(1, std::min<uint64_t>(k, plan.n));
     return (uint32_t)k;
 }
 
-EntropyJob make_job(const Plan& plan, const Tables& t, const uint8_t* d_payload_origin, uint32_t f0, uint32_t f1) {
+int decode_mode(const mjpeg423_b200_ctx* c, const Plan& plan) {
+    return plan.n_pframes ? std::max(1, c->staged) : c->staged;     // P frames need coefficient state in HBM
+}
+
+// Per-chunk scratch: block index (6 bytes per block) and, in the staged modes, coefficient planes.
+int reserve_chunk_buffers(mjpeg423_b200_ctx* c, const Plan& plan, uint32_t frames, int nbuf) {
+    const size_t blocks = (size_t)frames * 3 * plan.nb;
+    for (int i = 0; i < nbuf; i++) {
+        int rc = c->blkidx[i].reserve(blocks * 6 + 256);
+        if (rc) return rc;
+        if (decode_mode(c, plan) && (rc = c->coef[i].reserve(blocks * 128))) return rc;
+    }
+    if (decode_mode(c, plan) == 2) return c->samples.reserve(blocks * 64);
+    return MJPEG423_OK;
+}
+
+EntropyJob make_job(const Plan& plan, const Tables& t, const uint8_t* d_payload_origin, uint32_t f0, uint32_t f1,
+                    void* d_blkidx) {
     EntropyJob j;
     j.d_payload = d_payload_origin;
     j.d_streams = t.streams;
@@ -301,51 +361,71 @@ EntropyJob make_job(const Plan& plan, const Tables& t, const uint8_t* d_payload_
     j.n_write_tiles = plan.f_write0[f1] - plan.f_write0[f0];
     j.d_seg_entry = t.seg_entry; j.d_seg_exit = t.seg_exit; j.d_seg_cd = t.seg_cd; j.d_seg_first = t.seg_first;
     j.d_stream_blocks = t.stream_blocks; j.d_fixups = t.fixups;
+    // StreamDesc.block_base is plan-relative: shift the chunk buffers back by the chunk's first block
+    const size_t blocks = (size_t)(f1 - f0) * 3 * plan.nb, first_block = (size_t)f0 * 3 * plan.nb;
+    j.d_blk_pos = static_cast<uint32_t*>(d_blkidx) - first_block;
+    j.d_blk_dc = reinterpret_cast<int16_t*>(static_cast<uint32_t*>(d_blkidx) + blocks) - first_block;
     return j;
 }
 
-// Enqueue the whole decode of frames [f0, f1) on stream s.  d_coef is a buffer for (f1-f0) frames;
-// d_out receives (f1-f0) frames.  When prof != nullptr, events ev[0..4] bracket the stages.
+constexpr int N_PROF = 8;   // events per profiled chunk
+
+// Enqueue the whole decode of chunk `ch` on stream s; d_out receives its frames.  When prof != nullptr,
+// events prof[0..7] bracket the kernels (sync | chain | index | decode | idct | colour).
 int enqueue_chunk(mjpeg423_b200_ctx* c, const Plan& plan, const Tables& t, const uint8_t* d_payload_origin,
-                  uint32_t f0, uint32_t f1, int16_t* d_coef, void* d_out, cudaStream_t s, cudaEvent_t* prof) {
-    EntropyJob j = make_job(plan, t, d_payload_origin, f0, f1);
-    const size_t frame_blocks = (size_t)3 * plan.nb;
-    int16_t* coef_origin = d_coef - (size_t)f0 * frame_blocks * 64;    // StreamDesc.block_base is plan-relative
+                  const Chunk& ch, int buf, void* d_out, cudaStream_t s, cudaEvent_t* prof) {
+    const uint32_t f0 = ch.f0, f1 = ch.f1;
+    const int mode = decode_mode(c, plan);
+    EntropyJob j = make_job(plan, t, d_payload_origin, f0, f1, c->blkidx[buf].p);
     if (prof) CU(cudaEventRecord(prof[0], s));
     CU(launch_entropy_sync(j, s));
-    CU(launch_entropy_chain(j, s));
     if (prof) CU(cudaEventRecord(prof[1], s));
-    CU(launch_entropy_write(j, c->d_quant, coef_origin, s));
+    CU(launch_entropy_chain(j, s));
     if (prof) CU(cudaEventRecord(prof[2], s));
+    CU(launch_entropy_index(j, s));
+    if (prof) CU(cudaEventRecord(prof[3], s));
     c->stats.kernel_launches += 3;
-    if (c->staged) {
-        const size_t nblk = (size_t)(f1 - f0) * frame_blocks;
-        int rc = c->samples.reserve(nblk * 64);
-        if (rc) return rc;
-        CU(launch_idct(d_coef, c->samples.as<uint8_t>(), nblk, s));
-        if (prof) CU(cudaEventRecord(prof[3], s));
-        CU(launch_colour(c->samples.as<uint8_t>(), d_out, f1 - f0, plan.W, plan.H, s));
-        c->stats.kernel_launches += 2;
-    } else {
-        if (prof) CU(cudaEventRecord(prof[3], s));
-        CU(launch_idct_colour(d_coef, d_out, f1 - f0, plan.W, plan.H, s));
+    if (mode == 0) {
+        CU(launch_decode_fused(j, c->d_quant, d_out, f1 - f0, plan.W, plan.H, s));
+        c->stats.kernel_launches += 1;
+        if (prof) for (int k = 4; k < N_PROF; k++) CU(cudaEventRecord(prof[k], s));
+        return MJPEG423_OK;
+    }
+    int16_t* d_coef = c->coef[buf].as<int16_t>();
+    int16_t* coef_origin = d_coef - (size_t)f0 * 3 * plan.nb * 64;
+    const uint32_t* ids = c->ids.as<uint32_t>() + ch.ids_off;
+    for (size_t l = 0; l + 1 < ch.level_off.size(); l++) {       // one launch per GOP depth
+        CU(launch_decode_coef(j, ids + ch.level_off[l], ch.level_off[l + 1] - ch.level_off[l], plan.nb, c->d_quant,
+                              coef_origin, s));
         c->stats.kernel_launches += 1;
     }
     if (prof) CU(cudaEventRecord(prof[4], s));
+    if (mode == 2) {
+        CU(launch_idct(d_coef, c->samples.as<uint8_t>(), (size_t)(f1 - f0) * 3 * plan.nb, s));
+        if (prof) CU(cudaEventRecord(prof[5], s));
+        CU(launch_colour(c->samples.as<uint8_t>(), d_out, f1 - f0, plan.W, plan.H, s));
+        if (prof) { CU(cudaEventRecord(prof[6], s)); CU(cudaEventRecord(prof[7], s)); }
+        c->stats.kernel_launches += 2;
+    } else {
+        if (prof) { CU(cudaEventRecord(prof[5], s)); CU(cudaEventRecord(prof[6], s)); }
+        CU(launch_idct_colour(d_coef, d_out, f1 - f0, plan.W, plan.H, s));
+        if (prof) CU(cudaEventRecord(prof[7], s));
+        c->stats.kernel_launches += 1;
+    }
     return MJPEG423_OK;
 }
 
 int accumulate_profile(mjpeg423_b200_ctx* c, cudaEvent_t* prof) {
-    CU(cudaEventSynchronize(prof[4]));
-    float a = 0, b = 0, d = 0, e = 0;
-    CU(cudaEventElapsedTime(&a, prof[0], prof[1]));
-    CU(cudaEventElapsedTime(&b, prof[1], prof[2]));
-    CU(cudaEventElapsedTime(&d, prof[2], prof[3]));
-    CU(cudaEventElapsedTime(&e, prof[3], prof[4]));
-    c->stats.entropy_sync_ms += a;
-    c->stats.entropy_write_ms += b;
-    if (c->staged) { c->stats.idct_ms += d; c->stats.colour_ms += e; }
-    c->stats.idct_colour_ms += d + e;
+    CU(cudaEventSynchronize(prof[N_PROF - 1]));
+    float d[N_PROF - 1];
+    for (int k = 0; k + 1 < N_PROF; k++) CU(cudaEventElapsedTime(&d[k], prof[k], prof[k + 1]));
+    c->stats.sync_ms += d[0];
+    c->stats.chain_ms += d[1];
+    c->stats.index_ms += d[2];
+    c->stats.decode_ms += d[3];
+    c->stats.idct_ms += d[4];
+    c->stats.colour_ms += d[5];
+    c->stats.idct_colour_ms += d[6];
     return MJPEG423_OK;
 }
 
@@ -404,28 +484,30 @@ extern "C" int mjpeg423_b200_decode_resident(mjpeg423_b200_ctx* c, void* d_out) 
     if (plan.n == 0) return MJPEG423_OK;
     if (!d_out) return MJPEG423_E_ARG;
     Tables t = tables_of(c, plan);
-    const size_t coef_frame = (size_t)3 * plan.nb * 128;
-    const uint32_t K = c->chunk_frames ? std::min(c->chunk_frames, plan.n) : auto_chunk(plan, (uint64_t)3 << 30, coef_frame);
-    const uint32_t nchunks = (plan.n + K - 1) / K;
-    const int nbuf = (nchunks > 1 && !c->profile) ? 2 : 1;
-    for (int i = 0; i < nbuf; i++) { int rc = c->coef[i].reserve((size_t)K * coef_frame); if (rc) return rc; }
+    // chunk size: bounded scratch (block index 6 B/block, + 128 B/block of coefficients in the staged modes)
+    const size_t scratch_frame = (size_t)3 * plan.nb * (decode_mode(c, plan) ? 134 : 6);
+    const uint32_t K = c->chunk_frames ? std::min(c->chunk_frames, plan.n) : auto_chunk(plan, (uint64_t)3 << 30, scratch_frame);
+    int rc = prepare_chunks(c, plan, K, c->s_compute);
+    if (rc) return rc;
+    const int nbuf = (c->chunks.size() > 1 && !c->profile) ? 2 : 1;
+    if ((rc = reserve_chunk_buffers(c, plan, max_chunk_frames(c->chunks), nbuf))) return rc;
     cudaStream_t st[2] = {c->s_compute, c->s_aux};
     cudaEvent_t ev_start = c->ev[0], ev_stop = c->ev[1], ev_fork = c->ev[2], ev_join = c->ev[3];
     cudaEvent_t* prof = c->profile ? &c->ev[4] : nullptr;
     CU(cudaMemsetAsync(t.fixups, 0, 8, st[0]));
     CU(cudaEventRecord(ev_start, st[0]));
     if (nbuf == 2) { CU(cudaEventRecord(ev_fork, st[0])); CU(cudaStreamWaitEvent(st[1], ev_fork, 0)); }
-    for (uint32_t ch = 0; ch < nchunks; ch++) {
-        const uint32_t f0 = ch * K, f1 = std::min(plan.n, f0 + K);
-        const int b = (int)(ch % nbuf);
-        int rc = enqueue_chunk(c, plan, t, c->payload.as<uint8_t>(), f0, f1, c->coef[b].as<int16_t>(),
-                               (uint8_t*)d_out + (size_t)f0 * plan.nb * 256, st[b], prof);
+    for (size_t k = 0; k < c->chunks.size(); k++) {
+        const Chunk& ch = c->chunks[k];
+        const int b = (int)(k % nbuf);
+        rc = enqueue_chunk(c, plan, t, c->payload.as<uint8_t>(), ch, b, (uint8_t*)d_out + (size_t)ch.f0 * plan.nb * 256,
+                           st[b], prof);
         if (rc) return rc;
         if (prof) { rc = accumulate_profile(c, prof); if (rc) return rc; }
     }
     if (nbuf == 2) { CU(cudaEventRecord(ev_join, st[1])); CU(cudaStreamWaitEvent(st[0], ev_join, 0)); }
     CU(cudaEventRecord(ev_stop, st[0]));
-    int rc = finish_stats(c, plan, t, st[0]);
+    rc = finish_stats(c, plan, t, st[0]);
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ev_start, ev_stop));
     c->stats.total_ms = ms;
@@ -439,6 +521,7 @@ extern "C" int mjpeg423_b200_get_stats(mjpeg423_b200_ctx* c, mjpeg423_b200_stats
 }
 
 // ---- stage-level entry points on the resident job ------------------------------------------------------
+// lossless_decode() of every plane of every resident frame: d_coef = n x 3 x nb x 64 int16.
 extern "C" int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* c, int16_t* d_coef) {
     if (!c || !c->have_plan || !d_coef) return MJPEG423_E_ARG;
     CU(cudaSetDevice(c->device));
@@ -446,27 +529,40 @@ extern "C" int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* c, int16_t* d_c
     c->stats = mjpeg423_b200_stats{};
     if (plan.n == 0) return MJPEG423_OK;
     Tables t = tables_of(c, plan);
-    EntropyJob j = make_job(plan, t, c->payload.as<uint8_t>(), 0, plan.n);
     cudaStream_t s = c->s_compute;
+    int rc = prepare_chunks(c, plan, plan.n, s);          // one chunk: the caller's buffer holds every frame
+    if (rc) return rc;
+    if ((rc = c->blkidx[0].reserve((size_t)plan.n * 3 * plan.nb * 6 + 256))) return rc;
+    const Chunk& ch = c->chunks[0];
+    EntropyJob j = make_job(plan, t, c->payload.as<uint8_t>(), 0, plan.n, c->blkidx[0].p);
+    cudaEvent_t* e = &c->ev[4];
     CU(cudaMemsetAsync(t.fixups, 0, 8, s));
-    CU(cudaEventRecord(c->ev[0], s));
+    CU(cudaEventRecord(e[0], s));
     CU(launch_entropy_sync(j, s));
+    CU(cudaEventRecord(e[1], s));
     CU(launch_entropy_chain(j, s));
-    CU(cudaEventRecord(c->ev[2], s));
-    CU(launch_entropy_write(j, c->d_quant, d_coef, s));
-    CU(cudaEventRecord(c->ev[1], s));
-    c->stats.kernel_launches = 3;
-    int rc = finish_stats(c, plan, t, s);
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats.total_ms = ms;
-    CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[2])); c->stats.entropy_sync_ms = ms;
-    CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[1])); c->stats.entropy_write_ms = ms;
+    CU(cudaEventRecord(e[2], s));
+    CU(launch_entropy_index(j, s));
+    CU(cudaEventRecord(e[3], s));
+    const uint32_t* ids = c->ids.as<uint32_t>() + ch.ids_off;
+    for (size_t l = 0; l + 1 < ch.level_off.size(); l++) {
+        CU(launch_decode_coef(j, ids + ch.level_off[l], ch.level_off[l + 1] - ch.level_off[l], plan.nb, c->d_quant, d_coef, s));
+        c->stats.kernel_launches += 1;
+    }
+    CU(cudaEventRecord(e[4], s));
+    c->stats.kernel_launches += 3;
+    rc = finish_stats(c, plan, t, s);
+    CU(cudaEventElapsedTime(&c->stats.total_ms, e[0], e[4]));
+    CU(cudaEventElapsedTime(&c->stats.sync_ms, e[0], e[1]));
+    CU(cudaEventElapsedTime(&c->stats.chain_ms, e[1], e[2]));
+    CU(cudaEventElapsedTime(&c->stats.index_ms, e[2], e[3]));
+    CU(cudaEventElapsedTime(&c->stats.decode_ms, e[3], e[4]));
     return rc;
 }
 
 namespace {
 template <class F>
-int timed_stage(mjpeg423_b200_ctx* c, float* slot, F&& launch) {
+int timed_stage(mjpeg423_b200_ctx* c, float mjpeg423_b200_stats::*slot, F&& launch) {
     CU(cudaSetDevice(c->device));
     cudaStream_t s = c->s_compute;
     CU(cudaEventRecord(c->ev[0], s));
@@ -477,7 +573,7 @@ int timed_stage(mjpeg423_b200_ctx* c, float* slot, F&& launch) {
     CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
     c->stats = mjpeg423_b200_stats{};
     c->stats.total_ms = ms; c->stats.kernel_launches = 1; c->stats.frames = c->plan.n;
-    if (slot) *slot = ms;
+    c->stats.*slot = ms;
     return MJPEG423_OK;
 }
 }  // namespace
@@ -485,16 +581,16 @@ int timed_stage(mjpeg423_b200_ctx* c, float* slot, F&& launch) {
 extern "C" int mjpeg423_b200_resident_idct(mjpeg423_b200_ctx* c, const int16_t* d_coef, uint8_t* d_samples) {
     if (!c || !c->have_plan || !d_coef || !d_samples) return MJPEG423_E_ARG;
     const size_t nblk = (size_t)c->plan.n * 3 * c->plan.nb;
-    return timed_stage(c, &c->stats.idct_ms, [&](cudaStream_t s) { return launch_idct(d_coef, d_samples, nblk, s); });
+    return timed_stage(c, &mjpeg423_b200_stats::idct_ms, [&](cudaStream_t s) { return launch_idct(d_coef, d_samples, nblk, s); });
 }
 extern "C" int mjpeg423_b200_resident_colour(mjpeg423_b200_ctx* c, const uint8_t* d_samples, void* d_out) {
     if (!c || !c->have_plan || !d_samples || !d_out) return MJPEG423_E_ARG;
-    return timed_stage(c, &c->stats.colour_ms,
+    return timed_stage(c, &mjpeg423_b200_stats::colour_ms,
                        [&](cudaStream_t s) { return launch_colour(d_samples, d_out, c->plan.n, c->plan.W, c->plan.H, s); });
 }
 extern "C" int mjpeg423_b200_resident_idct_colour(mjpeg423_b200_ctx* c, const int16_t* d_coef, void* d_out) {
     if (!c || !c->have_plan || !d_coef || !d_out) return MJPEG423_E_ARG;
-    return timed_stage(c, &c->stats.idct_colour_ms, [&](cudaStream_t s) {
+    return timed_stage(c, &mjpeg423_b200_stats::idct_colour_ms, [&](cudaStream_t s) {
         return launch_idct_colour(d_coef, d_out, c->plan.n, c->plan.W, c->plan.H, s);
     });
 }
@@ -507,54 +603,53 @@ extern "C" int mjpeg423_b200_decode_frames(mjpeg423_b200_ctx* c, const uint8_t* 
     MpgIndex idx;
     int rc = parse_mpg(mpg, len, idx, false);
     if (rc) return rc;
-    Plan plan;
+    c->have_plan = false;                       // the resident tables are about to be overwritten
+    Plan& plan = c->plan;
     rc = build_plan(idx, first, n, plan);
     if (rc) return rc;
-    c->have_plan = false;                       // the resident tables are about to be overwritten
     c->stats = mjpeg423_b200_stats{};
     if (n == 0) return MJPEG423_OK;
     if (!out) return MJPEG423_E_ARG;
     Tables t;
     rc = upload_tables(c, plan, t, c->s_in);
     if (rc) return rc;
-    const size_t frame_bytes = (size_t)plan.nb * 256, coef_frame = (size_t)3 * plan.nb * 128;
+    const size_t frame_bytes = (size_t)plan.nb * 256;
     const uint32_t K = c->chunk_frames ? std::min(c->chunk_frames, n) : auto_chunk(plan, (uint64_t)512 << 20, frame_bytes);
-    const uint32_t nchunks = (n + K - 1) / K;
-    // Largest compressed chunk.
-    size_t max_in = 0;
-    for (uint32_t ch = 0; ch < nchunks; ch++) {
-        const uint32_t f0 = ch * K, f1 = std::min(n, f0 + K);
-        max_in = std::max<size_t>(max_in, plan.frames[f1 - 1].off + plan.frames[f1 - 1].size - plan.frames[f0].off);
-    }
+    if ((rc = prepare_chunks(c, plan, K, c->s_in))) return rc;
+    const uint32_t maxf = max_chunk_frames(c->chunks);
+    if ((rc = reserve_chunk_buffers(c, plan, maxf, 1))) return rc;
+    size_t max_in = 0;                                      // largest compressed chunk
+    for (const Chunk& ch : c->chunks)
+        max_in = std::max<size_t>(max_in, plan.frames[ch.f1 - 1].off + plan.frames[ch.f1 - 1].size - plan.frames[ch.f0].off);
     for (int i = 0; i < 2; i++) {
         if ((rc = c->in_ring[i].reserve(max_in + 64))) return rc;
-        if (!out_on_device && (rc = c->out_ring[i].reserve((size_t)K * frame_bytes))) return rc;
+        if (!out_on_device && (rc = c->out_ring[i].reserve((size_t)maxf * frame_bytes))) return rc;
     }
-    if ((rc = c->coef[0].reserve((size_t)K * coef_frame))) return rc;
     cudaEvent_t ev_start = c->ev[0], ev_stop = c->ev[1];
     cudaEvent_t* ev_in = &c->ev[2];     // [2]: payload slot uploaded
-    cudaEvent_t* ev_comp = &c->ev[4];   // [2]: chunk decoded (payload slot + out slot consumed/produced)
+    cudaEvent_t* ev_comp = &c->ev[4];   // [2]: chunk decoded (payload slot consumed, out slot produced)
     cudaEvent_t* ev_out = &c->ev[6];    // [2]: out slot read back
     cudaEvent_t* prof = c->profile ? &c->ev[8] : nullptr;
     CU(cudaMemsetAsync(t.fixups, 0, 8, c->s_in));
     CU(cudaEventRecord(ev_start, c->s_in));
     CU(cudaStreamWaitEvent(c->s_compute, ev_start, 0));
-    for (uint32_t ch = 0; ch < nchunks; ch++) {
-        const uint32_t f0 = ch * K, f1 = std::min(n, f0 + K);
-        const int b = (int)(ch & 1);
+    for (size_t k = 0; k < c->chunks.size(); k++) {
+        const Chunk& ch = c->chunks[k];
+        const uint32_t f0 = ch.f0, f1 = ch.f1;
+        const int b = (int)(k & 1);
         const uint64_t in_off = plan.frames[f0].off;
         const size_t in_len = plan.frames[f1 - 1].off + plan.frames[f1 - 1].size - in_off;
         // upload: the slot is free once the chunk that used it two iterations ago has been decoded
-        if (ch >= 2) CU(cudaStreamWaitEvent(c->s_in, ev_comp[b], 0));
+        if (k >= 2) CU(cudaStreamWaitEvent(c->s_in, ev_comp[b], 0));
         CU(cudaMemcpyAsync(c->in_ring[b].p, mpg + in_off, in_len, cudaMemcpyHostToDevice, c->s_in));
         CU(cudaMemsetAsync(c->in_ring[b].as<uint8_t>() + in_len, 0, 64, c->s_in));
         CU(cudaEventRecord(ev_in[b], c->s_in));
         // decode
         CU(cudaStreamWaitEvent(c->s_compute, ev_in[b], 0));
-        if (!out_on_device && ch >= 2) CU(cudaStreamWaitEvent(c->s_compute, ev_out[b], 0));
+        if (!out_on_device && k >= 2) CU(cudaStreamWaitEvent(c->s_compute, ev_out[b], 0));
         uint8_t* d_dst = out_on_device ? (uint8_t*)out + (size_t)f0 * frame_bytes : c->out_ring[b].as<uint8_t>();
         const uint8_t* origin = c->in_ring[b].as<uint8_t>() - (in_off - plan.payload_off);
-        rc = enqueue_chunk(c, plan, t, origin, f0, f1, c->coef[0].as<int16_t>(), d_dst, c->s_compute, prof);
+        rc = enqueue_chunk(c, plan, t, origin, ch, 0, d_dst, c->s_compute, prof);
         if (rc) return rc;
         CU(cudaEventRecord(ev_comp[b], c->s_compute));
         if (prof) { rc = accumulate_profile(c, prof); if (rc) return rc; }

@@ -25,11 +25,17 @@ struct EntropyJob {
     uint32_t *d_seg_entry = nullptr, *d_seg_exit = nullptr, *d_seg_cd = nullptr, *d_seg_first = nullptr; // plan-wide
     uint32_t* d_stream_blocks = nullptr;         // plan-wide, per stream
     unsigned long long* d_fixups = nullptr;
+    uint32_t* d_blk_pos = nullptr;               // block index, addressed by StreamDesc.block_base + b
+    int16_t* d_blk_dc = nullptr;
 };
 
 cudaError_t launch_entropy_sync(const EntropyJob& j, cudaStream_t s);
 cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s);
-cudaError_t launch_entropy_write(const EntropyJob& j, const int16_t* d_quant, int16_t* d_coef, cudaStream_t s);
+cudaError_t launch_entropy_index(const EntropyJob& j, cudaStream_t s);
+cudaError_t launch_decode_coef(const EntropyJob& j, const uint32_t* d_stream_ids, uint32_t n_ids, uint32_t nb,
+                               const int16_t* d_quant, int16_t* d_coef, cudaStream_t s);
+cudaError_t launch_decode_fused(const EntropyJob& j, const int16_t* d_quant, void* d_out, uint32_t n_frames,
+                                uint32_t W, uint32_t H, cudaStream_t s);
 cudaError_t launch_idct(const int16_t* d_coef, uint8_t* d_samples, size_t n_blocks, cudaStream_t s);
 cudaError_t launch_colour(const uint8_t* d_samples, void* d_out, uint32_t n_frames, uint32_t W, uint32_t H,
                           cudaStream_t s);
@@ -58,8 +64,19 @@ struct Plan {
     std::vector<TileDesc> sync_tiles, write_tiles;
     std::vector<uint32_t> f_sync0, f_write0, f_seg0;   // n+1 prefix tables per frame
     uint64_t stream_bytes = 0;                   // sum of plane stream lengths
+    uint32_t n_pframes = 0;
 };
 int build_plan(const MpgIndex& idx, uint32_t first, uint32_t n, Plan& plan);
+
+// A pipeline chunk: frames [f0, f1), always starting on an I frame.  P frames accumulate on the
+// previous frame's coefficients, so k_decode_coef runs once per GOP depth ("level"): level l holds the
+// streams of the frames that are l frames after their I frame.  ids_off indexes the uploaded id list.
+struct Chunk {
+    uint32_t f0 = 0, f1 = 0;
+    std::vector<uint32_t> level_off;             // size levels+1, offsets into the chunk's ids
+    uint32_t ids_off = 0;
+};
+void make_chunks(const Plan& plan, uint32_t K, std::vector<Chunk>& chunks, std::vector<uint32_t>& ids);
 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
@@ -79,7 +96,8 @@ struct mjpeg423_b200_ctx {
     int device = 0;
     cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr, s_aux = nullptr;
     // options
-    bool profile = false, staged = false, validate = true;
+    bool profile = false, validate = true;
+    int staged = 0;             // 0: fused decode, 1: coefficient planes + fused IDCT/colour, 2: all stages separate
     uint32_t chunk_frames = 0;
     // quant tables (2 x 64 int16, natural order) on device
     int16_t h_quant[128];
@@ -87,7 +105,9 @@ struct mjpeg423_b200_ctx {
     // resident job
     mj::Plan plan;
     bool have_plan = false;
-    DevBuf payload, tables, segs, coef[2], samples, stream_blocks, misc;
+    DevBuf payload, tables, segs, coef[2], blkidx[2], samples, stream_blocks, misc, ids;
+    std::vector<mj::Chunk> chunks;
+    uint32_t chunk_K = 0;
     // staging for the host-buffer path
     DevBuf in_ring[2], out_ring[2];
     void* h_stage[2] = {nullptr, nullptr};

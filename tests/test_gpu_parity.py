@@ -93,7 +93,7 @@ def test_golden_stage_functions(gold):
     assert np.array_equal(got, gold["ystream_coef"])
 
 
-@pytest.mark.parametrize("staged", [0, 1])
+@pytest.mark.parametrize("staged", [0, 1, 2])
 def test_golden_streams(gold, dec, staged):
     dec.set_option(api.OPT_STAGED, staged)
     try:
@@ -102,9 +102,11 @@ def test_golden_streams(gold, dec, staged):
         dec.set_quant(ones, ones)
         assert np.array_equal(dec.decode_frames(gold["mpg_dense"]), gold["frames_dense"])
         dec.set_quant(None, None)
-        info = mjpeg423_b200.probe(gold["mpg_ip"])
-        if info.num_pframes == 0:
-            assert np.array_equal(dec.decode_frames(gold["mpg_ip"]), gold["frames_ip"])
+        assert mjpeg423_b200.probe(gold["mpg_ip"]).num_pframes == 3          # I P P I P
+        assert np.array_equal(dec.decode_frames(gold["mpg_ip"]), gold["frames_ip"])
+        assert np.array_equal(dec.decode_frames(gold["mpg_ip"], first=3, n=2), gold["frames_ip"][3:])
+        with pytest.raises(RuntimeError, match="P frame"):
+            dec.decode_frames(gold["mpg_ip"], first=1, n=2)                   # a range must start on an I frame
     finally:
         dec.set_quant(None, None)
         dec.set_option(api.OPT_STAGED, 0)
@@ -268,6 +270,26 @@ def test_chunked_pipeline_matches_single_chunk(checker, dec):
         assert np.array_equal(dec.to_host(d_out, want.nbytes).reshape(want.shape), want), k
         dec.device_free(d_out)
     dec.set_option(api.OPT_CHUNK_FRAMES, 0)
+
+
+@pytest.mark.parametrize("gop,chunk", [(2, 0), (5, 3), (24, 7), (24, 1)])
+def test_pframe_streams(checker, dec, gop, chunk):
+    """P frames: coefficient-domain accumulation over the GOP (LIB/decoder/lossless_decode.c:90-92,121-123),
+    with chunk boundaries forced through the middle of GOPs (the pipeline must not split them)."""
+    W, H, n = 160, 96, 30
+    fr = np.stack([synth.synth_frame(W, H, i, 24) for i in range(n)])
+    mpg = synth.encode_mpg(fr, gop=gop)
+    want = checker.decode_mpg(mpg)
+    dec.set_option(api.OPT_CHUNK_FRAMES, chunk)
+    try:
+        assert np.array_equal(dec.decode_frames(mpg), want)
+        dec.upload(mpg)
+        d_out = dec.device_alloc(want.nbytes)
+        dec.decode_resident(d_out)
+        assert np.array_equal(dec.to_host(d_out, want.nbytes).reshape(want.shape), want)
+        dec.device_free(d_out)
+    finally:
+        dec.set_option(api.OPT_CHUNK_FRAMES, 0)
 
 
 def test_stage_entry_points(checker, dec):
