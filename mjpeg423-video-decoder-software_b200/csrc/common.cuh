@@ -56,12 +56,18 @@ struct BitReader {
     int nbits;             // valid bits in buf
 
     __device__ __forceinline__ void init(const uint8_t* base, uint32_t bitpos) {
-        uintptr_t a = reinterpret_cast<uintptr_t>(base) + (bitpos >> 3);
-        uint32_t skip = (uint32_t)(a & 3u) * 8u + (bitpos & 7u);
-        wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-        uint32_t w0 = __byte_perm(__ldg(wp), 0, 0x0123);
-        uint32_t w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);
-        wp += 2;
+        const uint32_t* p = word_ptr(base, bitpos);
+        init_loaded(base, bitpos, __ldg(p), __ldg(p + 1));
+    }
+    // Two-step form: fetch word_ptr()[0..1] early (e.g. for several streams at once), start later.
+    __device__ static __forceinline__ const uint32_t* word_ptr(const uint8_t* base, uint32_t bitpos) {
+        return reinterpret_cast<const uint32_t*>((reinterpret_cast<uintptr_t>(base) + (bitpos >> 3)) & ~(uintptr_t)3);
+    }
+    __device__ __forceinline__ void init_loaded(const uint8_t* base, uint32_t bitpos, uint32_t raw0, uint32_t raw1) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(base) + (bitpos >> 3);
+        const uint32_t skip = (uint32_t)(a & 3u) * 8u + (bitpos & 7u);
+        wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3) + 2;
+        const uint32_t w0 = __byte_perm(raw0, 0, 0x0123), w1 = __byte_perm(raw1, 0, 0x0123);
         buf = (((uint64_t)w0 << 32) | w1) << skip;
         nbits = 64 - (int)skip;
     }
@@ -153,38 +159,59 @@ struct Parser {
 // Single-block parser for the block-parallel decode kernels: the same trajectory function as
 // Parser::step, restricted to one block, delivering coefficients to a sink.
 // Sink::dc(e) / Sink::ac(zigzag_index, e).
+// WARP-COLLECTIVE: all 32 lanes must call it (lanes without a block pass active = false).  The symbol
+// loop runs under a warp vote so that the lanes re-converge every iteration; with independent thread
+// scheduling a plain data-dependent loop lets the warp fragment for good (profiles/r01b: 7 of 32 lanes
+// active per instruction).
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t FULL_MASK = 0xFFFFFFFFu;
+
 template <class Sink>
-__device__ __forceinline__ void parse_block(const uint8_t* base, uint32_t bitpos, uint32_t total_bits, Sink& sink) {
+__device__ __forceinline__ void parse_block_loaded(const uint8_t* base, uint32_t bitpos, uint32_t total_bits, Sink& sink,
+                                                   bool active, uint32_t raw0, uint32_t raw1);
+template <class Sink>
+__device__ __forceinline__ void parse_block(const uint8_t* base, uint32_t bitpos, uint32_t total_bits, Sink& sink,
+                                            bool active) {
+    const uint32_t* p0 = BitReader::word_ptr(base, active ? bitpos : 0u);
+    parse_block_loaded(base, bitpos, total_bits, sink, active, active ? __ldg(p0) : 0u, active ? __ldg(p0 + 1) : 0u);
+}
+template <class Sink>
+__device__ __forceinline__ void parse_block_loaded(const uint8_t* base, uint32_t bitpos, uint32_t total_bits, Sink& sink,
+                                                   bool active, uint32_t raw0, uint32_t raw1) {
     BitReader r;
-    r.init(base, bitpos);
-    const uint32_t max_bits = block_budget(bitpos, total_bits);
-    r.refill();
-    uint32_t t = r.top();
-    uint32_t size = t >> 28;
-    int e = 0;
-    if (size) e = vli_extend((t << 4) >> (32u - size), (int)size);
-    r.skip((int)(4u + size));
-    uint32_t used = 4u + size;
-    sink.dc(e);
-    uint32_t idx = 1;
-    while (used < max_bits) {
+    uint32_t max_bits = 0, used = 0, idx = 1;
+    if (active) {
+        r.init_loaded(base, bitpos, raw0, raw1);
+        max_bits = block_budget(bitpos, total_bits);
         r.refill();
-        t = r.top();
-        const uint32_t run = t >> 28;
-        size = (t >> 24) & 15u;
-        r.skip((int)(8u + size));
-        used += 8u + size;
-        if (size == 0) {
-            if (run != 15u) break;            // END
-            idx = (idx + 16u) & 255u;         // ZRL
-            continue;
+        const uint32_t t = r.top();
+        const uint32_t size = t >> 28;
+        int e = 0;
+        if (size) e = vli_extend((t << 4) >> (32u - size), (int)size);
+        r.skip((int)(4u + size));
+        used = 4u + size;
+        sink.dc(e);
+        active = used < max_bits;
+    }
+    while (__any_sync(FULL_MASK, active)) {
+        if (active) {
+            r.refill();
+            const uint32_t t = r.top();
+            const uint32_t run = t >> 28, size = (t >> 24) & 15u;
+            r.skip((int)(8u + size));
+            used += 8u + size;
+            if (size == 0) {
+                active = run == 15u;              // ZRL continues, END (any other run) stops
+                idx = (idx + 16u) & 255u;
+            } else {
+                const int e = vli_extend((t << 8) >> (32u - size), (int)size);
+                idx = (idx + run) & 255u;
+                if (idx < 64u) sink.ac(idx, e);
+                active = idx < 63u;
+                idx++;
+            }
+            active = active && used < max_bits;
         }
-        e = vli_extend((t << 8) >> (32u - size), (int)size);
-        idx = (idx + run) & 255u;
-        if (idx < 64u) sink.ac(idx, e);
-        if (idx >= 63u) break;
-        idx++;
     }
 }
 
@@ -224,7 +251,8 @@ __device__ __forceinline__ void idct8(int i0, int i1, int i2, int i3, int i4, in
 
 __device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xFFFFu); }
 __device__ __forceinline__ int hi16(uint32_t w) { return (int)w >> 16; }
-__device__ __forceinline__ uint32_t clamp255(int v) { return (uint32_t)min(max(v, 0), 255); }  // NORMALIZE, idct.c:20
+// NORMALIZE, idct.c:20: max(min(v, 255), 0) -- one VIMNMX.RELU.
+__device__ __forceinline__ uint32_t clamp255(int v) { return (uint32_t)__vimin_s32_relu(v, 255); }
 
 // Column occupancy of a block held as 8 rows of packed int16: bit c of `ac` is set when column c has a
 // non-zero coefficient in rows 1..7, bit c of `any` when it has one in any row.
@@ -297,17 +325,18 @@ __device__ __forceinline__ void idct_block(const uint4 (&rows)[8], uint32_t acma
 __device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_sync(0xFFFFFFFFu, v); }
 
 // YCbCr -> packed BGRA word: LIB/decoder/ycbcr_to_rgb.c:31-46.  NORMALIZE_RGB (:19): negative -> 0,
-// else >> 14 then cap at 255.  Word = B | G<<8 | R<<16 | A(0)<<24 (rgb_pixel_t, mjpeg423_types.h:56-61).
+// else >> 14 then cap at 255 == relu(min(t >> 14, 255)) (an arithmetic shift keeps the sign).
+// Word = B | G<<8 | R<<16 | A(0)<<24 (rgb_pixel_t, mjpeg423_types.h:56-61).
+// The "- 128" of Cb/Cr is folded into the constant term: (Y<<14) + k*(C-128) == Y*16384 + k*C - 128*k,
+// all exact in int32 (|value| < 2^24).
 __device__ __forceinline__ uint32_t ycc_to_bgra(uint32_t y, uint32_t cb, uint32_t cr) {
-    int cbb = (int)cb - 128, crr = (int)cr - 128;
-    int yy = (int)(y << 14);
-    int r = yy + 22970 * crr;
-    int g = yy - 5638 * cbb - 11700 * crr;
-    int b = yy + 29032 * cbb;
-    // max(t,0) >> 14 then min(.,255) == NORMALIZE_RGB
-    uint32_t R = (uint32_t)min(max(r, 0) >> 14, 255);
-    uint32_t G = (uint32_t)min(max(g, 0) >> 14, 255);
-    uint32_t B = (uint32_t)min(max(b, 0) >> 14, 255);
+    const int Y = (int)y, CB = (int)cb, CR = (int)cr;
+    const int r = Y * 16384 + 22970 * CR - 128 * 22970;
+    const int g = Y * 16384 - 5638 * CB - 11700 * CR + 128 * (5638 + 11700);
+    const int b = Y * 16384 + 29032 * CB - 128 * 29032;
+    const uint32_t R = (uint32_t)__vimin_s32_relu(r >> 14, 255);
+    const uint32_t G = (uint32_t)__vimin_s32_relu(g >> 14, 255);
+    const uint32_t B = (uint32_t)__vimin_s32_relu(b >> 14, 255);
     return B | (G << 8) | (R << 16);
 }
 

@@ -104,18 +104,17 @@ k_decode_coef(const uint8_t* __restrict__ payload, const StreamDesc* __restrict_
         zero_slot(slots, t);
     }
     __syncthreads();
-    if ((uint32_t)t < nblk) {
+    {
         const uint32_t gb = sd.block_base + b0 + (uint32_t)t;
-        const uint32_t pos = blk_pos[gb];
-        if (pos != NO_BLOCK) {
-            const uint8_t* base = payload + sd.byte_off;
-            if (sd.ptype) {
-                SlotSink<true> sink{slots, s_zq, t, 0, 0, 0};
-                parse_block(base, pos, sd.byte_len * 8u, sink);
-            } else {
-                SlotSink<false> sink{slots, s_zq, t, (int)blk_dc[gb], 0, 0};
-                parse_block(base, pos, sd.byte_len * 8u, sink);
-            }
+        const bool have = (uint32_t)t < nblk;
+        const uint32_t pos = have ? blk_pos[gb] : NO_BLOCK;
+        const uint8_t* base = payload + sd.byte_off;
+        if (sd.ptype) {
+            SlotSink<true> sink{slots, s_zq, t, 0, 0, 0};
+            parse_block(base, pos, sd.byte_len * 8u, sink, pos != NO_BLOCK);
+        } else {
+            SlotSink<false> sink{slots, s_zq, t, have ? (int)blk_dc[gb] : 0, 0, 0};
+            parse_block(base, pos, sd.byte_len * 8u, sink, pos != NO_BLOCK);
         }
     }
     __syncthreads();
@@ -126,46 +125,157 @@ k_decode_coef(const uint8_t* __restrict__ payload, const StreamDesc* __restrict_
 }
 
 // ---- fully fused: bitstream + block index -> BGRA ---------------------------------------------------------
-// grid = (ceil(nb / 128), frames); streams of frame f are streams[stream_lo + 3f + {0,1,2}].
-__global__ void __launch_bounds__(DEC_TPB, 4)
+// PERSISTENT kernel: one CTA of FUSED_TPB threads per SM (all the shared memory of the SM), every WARP
+// loops over warp tiles of 32 consecutive block positions of one frame.  Warps never synchronise with
+// each other after the table set-up, so a warp that finishes a cheap tile (flat picture area) starts the
+// next one at once and the SM stays at its full 14 resident warps.
+//
+// The body is written as LOOPS over planes, column pairs and rows with its working set in shared
+// memory, not as one unrolled register-resident IDCT: warps drift apart in the data-dependent parse,
+// so the instruction working set has to fit the instruction cache (the unrolled form is ~100 KB of
+// SASS and ran instruction-fetch bound, profiles/r01b).  Shared memory (word-interleaved by thread so
+// that every access below is bank-conflict free; T = FUSED_TPB):
+//   coef  uint4 [8][T]    chunk c = column c of the block: rows 0..7 as int16 (the parser scatters
+//                         straight into this TRANSPOSED layout, so pass 1 reads a column with one LDS.128)
+//   ws    uint2 [32][T]   unit r*4 + c/2 = pass-1 outputs ws[r][c], ws[r][c+1] (int32)
+//   stash u32   [32][T]   word p*16 + 2r + h = samples of plane p (Y, Cb), row r, half h
+constexpr int FUSED_TPB = 448;                                   // 14 warps x 512 B/thread = 224 KB of the SM's 227 KB
+constexpr int FUSED_SMEM = FUSED_TPB * (128 + 256 + 128) + 2 * 64 * 4;
+
+struct FusedSink {              // parse_block() sink: dequantise, scatter transposed, track occupancy
+    uint8_t* coef;              // this thread's base: coef + t*16
+    const uint32_t* zq;         // smem: transposed byte offset | quant << 16, by zig-zag position
+    int cur;
+    uint32_t m_ac, m_any;
+    __device__ __forceinline__ void dc(int) {
+        *reinterpret_cast<int16_t*>(coef) = (int16_t)((int)(int16_t)cur * (int)(zq[0] >> 16));   // lossless_decode.c:94-95
+        m_any |= 1u;
+    }
+    __device__ __forceinline__ void ac(uint32_t idx, int e) {
+        const uint32_t z = zq[idx];
+        const uint32_t off = z & 0xFFFFu;                       // column * (T*16) + row * 2
+        *reinterpret_cast<int16_t*>(coef + off) = (int16_t)(e * (int)(z >> 16));              // :125
+        const uint32_t col = off / (FUSED_TPB * 16u);
+        m_any |= 1u << col;
+        if (off & 15u) m_ac |= 1u << col;                       // row >= 1
+    }
+};
+
+__global__ void __launch_bounds__(FUSED_TPB, 1)
 k_decode_fused(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
                const uint32_t* __restrict__ blk_pos, const int16_t* __restrict__ blk_dc,
-               const int16_t* __restrict__ quant, uint8_t* __restrict__ out, uint32_t nb, uint32_t wb, uint32_t W) {
-    __shared__ __align__(128) uint8_t slots[DEC_TPB * 128];
-    __shared__ uint32_t s_zq[2][64];
+               const int16_t* __restrict__ quant, uint8_t* __restrict__ out, uint32_t nb, uint32_t wb, uint32_t W,
+               uint32_t n_frames) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_coef = smem;
+    uint2* s_ws = reinterpret_cast<uint2*>(smem + FUSED_TPB * 128);
+    uint32_t* s_stash = reinterpret_cast<uint32_t*>(smem + FUSED_TPB * 384);
+    uint32_t* s_zq = reinterpret_cast<uint32_t*>(smem + FUSED_TPB * 512);    // 2 x 64 words
     const int t = threadIdx.x;
-    const uint32_t f = blockIdx.y;
-    const uint32_t b = blockIdx.x * DEC_TPB + (uint32_t)t;
-    const bool live = b < nb;
-    load_zq(s_zq[0], quant, t);
-    load_zq(s_zq[1], quant + 64, t);
+    if (t < 128) {                                                       // zig-zag -> transposed offset | quant
+        const int tab = t >> 6, k = t & 63;
+        const uint32_t n = c_zigzag[k];
+        s_zq[t] = ((n & 7u) * (FUSED_TPB * 16u) + (n >> 3) * 2u) | ((uint32_t)(uint16_t)quant[tab * 64 + n] << 16);
+    }
     __syncthreads();
-    uint32_t px[3][16];
+    uint8_t* my_coef = s_coef + t * 16;
+    const uint32_t tiles_per_frame = (nb + 31u) / 32u;
+    const uint32_t n_tiles = tiles_per_frame * n_frames;
+    const uint32_t warps_per_cta = FUSED_TPB / 32;
+
+    for (uint32_t tile = blockIdx.x * warps_per_cta + (uint32_t)(t >> 5); tile < n_tiles; tile += gridDim.x * warps_per_cta) {
+        const uint32_t f = tile / tiles_per_frame;
+        const uint32_t b = (tile - f * tiles_per_frame) * 32u + (uint32_t)(t & 31);
+        const bool live = b < nb;
+        const StreamDesc* sd0 = streams + (size_t)f * 3;
+        uint8_t* dst = out + ((size_t)f * nb * 64 + ((size_t)(b / wb) * 8 * W + (size_t)(b % wb) * 8)) * 4;
+
+        // Fetch the index entries and the first two bitstream words of all three planes up front: the
+        // three dependent global round trips overlap instead of serialising in front of each parse.
+        uint32_t pos[3], raw0[3], raw1[3];
+        int dcl[3];
 #pragma unroll
-    for (int p = 0; p < 3; p++) {
-        const StreamDesc* sd = streams + (size_t)f * 3 + p;
-        zero_slot(slots, t);                                    // thread-private slot: no barrier needed
-        SlotSink<false> sink{slots, s_zq[p ? 1 : 0], t, 0, 0, 0};
-        if (live) {
-            const uint32_t gb = sd->block_base + b;
-            const uint32_t pos = blk_pos[gb];
-            if (pos != NO_BLOCK) {
-                sink.cur = (int)blk_dc[gb];
-                parse_block(payload + sd->byte_off, pos, sd->byte_len * 8u, sink);
+        for (int p = 0; p < 3; p++) {
+            const uint32_t gb = sd0[p].block_base + b;
+            pos[p] = live ? blk_pos[gb] : NO_BLOCK;
+            dcl[p] = live ? (int)blk_dc[gb] : 0;
+        }
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            const bool have = pos[p] != NO_BLOCK;
+            const uint32_t* wp = BitReader::word_ptr(payload + sd0[p].byte_off, have ? pos[p] : 0u);
+            raw0[p] = have ? __ldg(wp) : 0u;
+            raw1[p] = have ? __ldg(wp + 1) : 0u;
+        }
+
+#pragma unroll 1
+        for (int p = 0; p < 3; p++) {
+            // ---- parse this plane's block into the (zeroed) transposed coefficient slot -------------------
+#pragma unroll
+            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(my_coef + c * (FUSED_TPB * 16)) = make_uint4(0, 0, 0, 0);
+            // (p is a loop variable: select the pre-fetched registers without dynamic indexing)
+            const uint32_t ppos = p == 0 ? pos[0] : p == 1 ? pos[1] : pos[2];
+            const uint32_t pr0 = p == 0 ? raw0[0] : p == 1 ? raw0[1] : raw0[2];
+            const uint32_t pr1 = p == 0 ? raw1[0] : p == 1 ? raw1[1] : raw1[2];
+            FusedSink sink{my_coef, s_zq + (p ? 64 : 0), p == 0 ? dcl[0] : p == 1 ? dcl[1] : dcl[2], 0, 0};
+            parse_block_loaded(payload + sd0[p].byte_off, ppos, sd0[p].byte_len * 8u, sink, ppos != NO_BLOCK, pr0, pr1);
+            const uint32_t acm = warp_or(sink.m_ac), anym = warp_or(sink.m_any);    // warp-uniform from here on
+
+            // emit(r, w0, w1): Y and Cb rows go to the stash, a Cr row completes 8 pixels.
+            auto emit = [&](int r, uint32_t w0, uint32_t w1) {
+                if (p < 2) {
+                    s_stash[(p * 16 + 2 * r) * FUSED_TPB + t] = w0;
+                    s_stash[(p * 16 + 2 * r + 1) * FUSED_TPB + t] = w1;
+                } else if (live) {
+                    colour_row_store(s_stash[(2 * r) * FUSED_TPB + t], s_stash[(2 * r + 1) * FUSED_TPB + t],
+                                     s_stash[(16 + 2 * r) * FUSED_TPB + t], s_stash[(17 + 2 * r) * FUSED_TPB + t], w0, w1,
+                                     dst + (size_t)r * W * 4);
+                }
+            };
+
+            if (((anym & 0xFEu) | (acm & 1u)) == 0) {
+                // DC-only blocks in the whole warp: both passes collapse to (4*dc + 16) >> 5 (see idct_block()).
+                const int dcv = (int)*reinterpret_cast<const int16_t*>(my_coef);
+                const uint32_t v = clamp255(((dcv << 2) + 16) >> 5) * 0x01010101u;
+#pragma unroll 1
+                for (int r = 0; r < 8; r++) emit(r, v, v);
+                continue;
+            }
+            // ---- pass 1: columns, two at a time (idct.c:41-109) --------------------------------------------------
+            const bool high_half = (anym & 0xF0u) != 0;
+            const int npair = high_half ? 4 : 2;
+#pragma unroll 1
+            for (int cp = 0; cp < npair; cp++) {
+                const uint4 c0 = *reinterpret_cast<const uint4*>(my_coef + (2 * cp) * (FUSED_TPB * 16));
+                const uint4 c1 = *reinterpret_cast<const uint4*>(my_coef + (2 * cp + 1) * (FUSED_TPB * 16));
+                int o0[8], o1[8];
+                if ((acm >> (2 * cp)) & 3u) {
+                    idct8<11>(lo16(c0.x), hi16(c0.x), lo16(c0.y), hi16(c0.y), lo16(c0.z), hi16(c0.z), lo16(c0.w), hi16(c0.w), o0);
+                    idct8<11>(lo16(c1.x), hi16(c1.x), lo16(c1.y), hi16(c1.y), lo16(c1.z), hi16(c1.z), lo16(c1.w), hi16(c1.w), o1);
+                } else {                                        // no AC in either column: DESCALE(in0 << 13, 11) == in0 << 2
+                    const int v0 = (int)((unsigned)lo16(c0.x) << 2), v1 = (int)((unsigned)lo16(c1.x) << 2);
+#pragma unroll
+                    for (int r = 0; r < 8; r++) { o0[r] = v0; o1[r] = v1; }
+                }
+#pragma unroll
+                for (int r = 0; r < 8; r++) s_ws[(r * 4 + cp) * FUSED_TPB + t] = make_uint2((uint32_t)o0[r], (uint32_t)o1[r]);
+            }
+            // ---- pass 2: rows (idct.c:116-180) ------------------------------------------------------------------
+#pragma unroll 1
+            for (int r = 0; r < 8; r++) {
+                const uint2 a = s_ws[(r * 4 + 0) * FUSED_TPB + t], bq = s_ws[(r * 4 + 1) * FUSED_TPB + t];
+                int o[8];
+                if (high_half) {
+                    const uint2 cq = s_ws[(r * 4 + 2) * FUSED_TPB + t], dq = s_ws[(r * 4 + 3) * FUSED_TPB + t];
+                    idct8<18>((int)a.x, (int)a.y, (int)bq.x, (int)bq.y, (int)cq.x, (int)cq.y, (int)dq.x, (int)dq.y, o);
+                } else {
+                    idct8<18>((int)a.x, (int)a.y, (int)bq.x, (int)bq.y, 0, 0, 0, 0, o);
+                }
+                emit(r, clamp255(o[0]) | (clamp255(o[1]) << 8) | (clamp255(o[2]) << 16) | (clamp255(o[3]) << 24),
+                     clamp255(o[4]) | (clamp255(o[5]) << 8) | (clamp255(o[6]) << 16) | (clamp255(o[7]) << 24));
             }
         }
-        __syncwarp();
-        const uint32_t acm = warp_or(sink.m_ac), anym = warp_or(sink.m_any);
-        uint4 rows[8];
-        load_slot_rows(slots, t, rows);
-        idct_block(rows, acm, anym, px[p]);
     }
-    if (!live) return;
-    uint8_t* dst = out + ((size_t)f * nb * 64 + ((size_t)(b / wb) * 8 * W + (size_t)(b % wb) * 8)) * 4;
-#pragma unroll
-    for (int r = 0; r < 8; r++)
-        colour_row_store(px[0][2 * r], px[0][2 * r + 1], px[1][2 * r], px[1][2 * r + 1], px[2][2 * r], px[2][2 * r + 1],
-                         dst + (size_t)r * W * 4);
 }
 
 // ---- launchers -----------------------------------------------------------------------------------------------
@@ -179,10 +289,20 @@ cudaError_t launch_decode_coef(const EntropyJob& j, const uint32_t* d_stream_ids
 cudaError_t launch_decode_fused(const EntropyJob& j, const int16_t* d_quant, void* d_out, uint32_t n_frames,
                                 uint32_t W, uint32_t H, cudaStream_t s) {
     if (n_frames == 0) return cudaSuccess;
+    static int n_sm = 0;
+    if (!n_sm) {
+        cudaError_t e = cudaFuncSetAttribute(k_decode_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
+        if (e != cudaSuccess) return e;
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    }
     const uint32_t wb = W / 8, nb = wb * (H / 8);
-    dim3 grid((nb + DEC_TPB - 1) / DEC_TPB, n_frames);
-    k_decode_fused<<<grid, DEC_TPB, 0, s>>>(j.d_payload, j.d_streams + j.stream_lo, j.d_blk_pos, j.d_blk_dc, d_quant,
-                                            (uint8_t*)d_out, nb, wb, W);
+    const uint64_t n_tiles = (uint64_t)((nb + 31) / 32) * n_frames;
+    const uint64_t want = (n_tiles + FUSED_TPB / 32 - 1) / (FUSED_TPB / 32);
+    const unsigned grid = (unsigned)(want < (uint64_t)n_sm ? want : (uint64_t)n_sm);     // persistent: one CTA per SM
+    k_decode_fused<<<grid, FUSED_TPB, FUSED_SMEM, s>>>(j.d_payload, j.d_streams + j.stream_lo, j.d_blk_pos, j.d_blk_dc,
+                                                       d_quant, (uint8_t*)d_out, nb, wb, W, n_frames);
     return cudaGetLastError();
 }
 

@@ -59,53 +59,60 @@ __device__ __forceinline__ uint32_t parse_segment(const uint8_t* base, uint32_t 
 struct Resolved { uint32_t exit_pos, cnt, dc; };
 
 // Resolve segment [seg_start, seg_end) for true entry E against the recorded speculative trajectory.
+// WARP-COLLECTIVE (lanes with nothing to resolve pass need = false): the symbol loop runs under a warp
+// vote so the lanes re-converge every iteration.
 __device__ __forceinline__ Resolved resolve_by_merge(const uint8_t* base, uint32_t E, uint32_t seg_start,
                                                      uint32_t seg_end, uint32_t total_bits,
                                                      const uint32_t (*s_pos)[ENT_TPB], const uint32_t (*s_cd)[ENT_TPB],
-                                                     int t) {
+                                                     int t, bool need) {
     const uint32_t spec_exit = s_pos[NCP - 1][t], spec_cd = s_cd[NCP - 1][t];
     Resolved rs{E, 0, 0};
-    if (E >= seg_end) return rs;                         // a block spans the whole segment: it owns nothing
-    if (E == seg_start) {                                // speculation started on the true entry
+    bool active = need;
+    if (active && (E >= seg_end || E + MIN_BLOCK_BITS > total_bits)) active = false;   // owns nothing
+    if (active && E == seg_start) {                      // speculation started on the true entry
         rs.exit_pos = spec_exit; rs.cnt = spec_cd & 0xFFFFu; rs.dc = spec_cd >> 16;
-        return rs;
+        active = false;
     }
-    if (E + MIN_BLOCK_BITS > total_bits) return rs;
-    if (E >= seg_start + CP_BITS) {                      // E itself may be a recorded block start
+    if (active && E >= seg_start + CP_BITS) {            // E itself may be a recorded block start
         const int j = (int)((E - seg_start) / CP_BITS) - 1;
         if (s_pos[j][t] == E) {
             const uint32_t at = s_cd[j][t];
             rs.exit_pos = spec_exit;
             rs.cnt = (spec_cd & 0xFFFFu) - (at & 0xFFFFu);
             rs.dc = ((spec_cd >> 16) - (at >> 16)) & 0xFFFFu;
-            return rs;
+            active = false;
         }
     }
     Parser ps;
-    ps.start(base, E, total_bits);
+    if (active) ps.start(base, E, total_bits);
     int dcsum = 0;
     uint32_t cnt = 0;
-    for (;;) {
-        int e;
-        const bool end = ps.step(total_bits, e);
-        dcsum += e;
-        if (!end) continue;
-        cnt++;
-        const uint32_t pos = ps.pos;
-        if (pos >= seg_start + CP_BITS) {
-            const int j = (int)min((uint32_t)NCP, (pos - seg_start) / CP_BITS) - 1;
-            if (s_pos[j][t] == pos) {                    // merged with the speculative trajectory
-                const uint32_t at = s_cd[j][t];
-                cnt += (spec_cd & 0xFFFFu) - (at & 0xFFFFu);
-                dcsum += (int)(spec_cd >> 16) - (int)(at >> 16);
-                rs.exit_pos = spec_exit;
-                break;
+    const bool parsed = active;
+    while (__any_sync(FULL_MASK, active)) {
+        if (active) {
+            int e;
+            const bool end = ps.step(total_bits, e);
+            dcsum += e;
+            if (end) {
+                cnt++;
+                const uint32_t pos = ps.pos;
+                bool merged = false;
+                if (pos >= seg_start + CP_BITS) {
+                    const int j = (int)min((uint32_t)NCP, (pos - seg_start) / CP_BITS) - 1;
+                    if (s_pos[j][t] == pos) {            // merged with the speculative trajectory
+                        const uint32_t at = s_cd[j][t];
+                        cnt += (spec_cd & 0xFFFFu) - (at & 0xFFFFu);
+                        dcsum += (int)(spec_cd >> 16) - (int)(at >> 16);
+                        rs.exit_pos = spec_exit;
+                        merged = true;
+                    }
+                }
+                if (merged) active = false;
+                else if (pos >= seg_end || pos + MIN_BLOCK_BITS > total_bits) { rs.exit_pos = pos; active = false; }
             }
         }
-        if (pos >= seg_end || pos + MIN_BLOCK_BITS > total_bits) { rs.exit_pos = pos; break; }
     }
-    rs.cnt = cnt;
-    rs.dc = (uint32_t)dcsum & 0xFFFFu;
+    if (parsed) { rs.cnt = cnt; rs.dc = (uint32_t)dcsum & 0xFFFFu; }
     return rs;
 }
 
@@ -126,52 +133,51 @@ k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
     const uint32_t seg_start = (uint32_t)seg * SEG_BITS, seg_end = seg_start + SEG_BITS;
 
     // ---- speculative parse from the segment's first bit --------------------------------------------
-    if (valid) {
+    {
         int j = 0;
         uint32_t cnt = 0;
         int dcsum = 0;
         uint32_t pos = seg_start;
-        if (pos + MIN_BLOCK_BITS <= total_bits) {
-            Parser ps;
-            ps.start(base, seg_start, total_bits);
-            uint32_t next_cp = seg_start + CP_BITS;
-            for (;;) {
+        bool active = valid && pos + MIN_BLOCK_BITS <= total_bits;
+        Parser ps;
+        if (active) ps.start(base, seg_start, total_bits);
+        uint32_t next_cp = seg_start + CP_BITS;
+        while (__any_sync(FULL_MASK, active)) {
+            if (active) {
                 int e;
                 const bool end = ps.step(total_bits, e);
                 dcsum += e;
-                if (!end) continue;
-                cnt++;
-                pos = ps.pos;
-                if (pos >= next_cp) {
-                    const uint32_t rec = cnt | ((uint32_t)dcsum << 16);
-                    do { s_pos[j][t] = pos; s_cd[j][t] = rec; j++; next_cp += CP_BITS; } while (j < NCP && pos >= next_cp);
-                    if (j == NCP) break;
+                if (end) {
+                    cnt++;
+                    pos = ps.pos;
+                    if (pos >= next_cp) {
+                        const uint32_t rec = cnt | ((uint32_t)dcsum << 16);
+                        do { s_pos[j][t] = pos; s_cd[j][t] = rec; j++; next_cp += CP_BITS; } while (j < NCP && pos >= next_cp);
+                        if (j == NCP) active = false;
+                    }
+                    if (pos + MIN_BLOCK_BITS > total_bits) active = false;   // end of stream: no further block can start
                 }
-                if (pos + MIN_BLOCK_BITS > total_bits) break;     // end of stream: no further block can start
             }
         }
-        const uint32_t rec = cnt | ((uint32_t)dcsum << 16);
-        for (; j < NCP; j++) { s_pos[j][t] = pos; s_cd[j][t] = rec; }
+        if (valid) {
+            const uint32_t rec = cnt | ((uint32_t)dcsum << 16);
+            for (; j < NCP; j++) { s_pos[j][t] = pos; s_cd[j][t] = rec; }
+        }
     }
     __syncthreads();
 
     // ---- round 1: entry = predecessor's speculative exit -------------------------------------------------
     const bool own = valid && t >= 1;
-    uint32_t E = 0;
-    Resolved rs{0, 0, 0};
-    if (own) {
-        E = seg == 0 ? 0u : s_pos[NCP - 1][t - 1];
-        rs = resolve_by_merge(base, E, seg_start, seg_end, total_bits, s_pos, s_cd, t);
-    }
+    uint32_t E = (own && seg != 0) ? s_pos[NCP - 1][t - 1] : 0u;
+    Resolved rs = resolve_by_merge(base, E, seg_start, seg_end, total_bits, s_pos, s_cd, t, own);
     s_rexit[t] = own ? rs.exit_pos : (valid ? s_pos[NCP - 1][t] : 0u);   // the halo keeps its speculative exit
     __syncthreads();
     // ---- round 2: re-merge where the predecessor's resolved exit differs from its speculative one ----------
-    if (own && seg != 0) {
-        const uint32_t E2 = s_rexit[t - 1];
-        if (E2 != E) {
-            E = E2;
-            rs = resolve_by_merge(base, E, seg_start, seg_end, total_bits, s_pos, s_cd, t);
-        }
+    {
+        const uint32_t E2 = (own && seg != 0) ? s_rexit[t - 1] : E;
+        const bool redo = own && E2 != E;
+        const Resolved r2 = resolve_by_merge(base, E2, seg_start, seg_end, total_bits, s_pos, s_cd, t, redo);
+        if (redo) { E = E2; rs = r2; }
     }
     if (own) {
         const uint32_t g = sd.seg_base + (uint32_t)seg;
@@ -262,32 +268,33 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
     const TileDesc td = tiles[blockIdx.x];
     const StreamDesc sd = streams[td.stream];
     const uint32_t seg = td.seg0 + (uint32_t)t;
-    if (seg >= sd.nseg) return;
+    const bool valid = seg < sd.nseg;
     const uint8_t* base = payload + sd.byte_off;
     const uint32_t total_bits = sd.byte_len * 8u;
-    const uint32_t g = sd.seg_base + seg;
-    const uint32_t first = seg_first[g];
-    const uint32_t cd = seg_cd[g];
+    const uint32_t g = sd.seg_base + (valid ? seg : 0u);
+    const uint32_t first = valid ? seg_first[g] : 0u;
+    const uint32_t cd = valid ? seg_cd[g] : 0u;
     uint32_t cnt = cd & 0xFFFFu;
     cnt = first >= sd.nb ? 0u : min(cnt, sd.nb - first);          // trailing pad bits can look like blocks
     uint32_t* bp = blk_pos + sd.block_base + first;
     int16_t* bd = blk_dc + sd.block_base + first;
-    if (cnt) {
-        Parser ps;
-        ps.start(base, seg_entry[g], total_bits);
-        int cur = (int)(cd >> 16);
-        uint32_t k = 0;
-        for (;;) {
+    bool active = valid && cnt != 0;
+    Parser ps;
+    if (active) ps.start(base, seg_entry[g], total_bits);
+    int cur = (int)(cd >> 16);
+    uint32_t k = 0;
+    while (__any_sync(FULL_MASK, active)) {
+        if (active) {
             const bool was_dc = ps.is_dc;
             const uint32_t at = ps.pos;
             int e;
             const bool end = ps.step(total_bits, e);
             if (was_dc) { cur += e; bp[k] = at; bd[k] = (int16_t)cur; }
-            if (end && ++k == cnt) break;
+            if (end && ++k == cnt) active = false;
         }
     }
     // A stream that ends early leaves the remaining blocks empty (zero coefficients).
-    if (seg + 1 == sd.nseg)
+    if (valid && seg + 1 == sd.nseg)
         for (uint32_t b = first + cnt; b < sd.nb; b++) { blk_pos[sd.block_base + b] = NO_BLOCK; blk_dc[sd.block_base + b] = 0; }
 }
 
