@@ -45,55 +45,62 @@ struct TileDesc {
 };
 
 // ------------------------------------------------------------------------------------------------
-// MSB-first bit reader over global memory: 64-bit window, refilled by aligned 32-bit words.
-// Replaces update_buffer / INPUT_BITS (LIB/decoder/lossless_decode.c:139-162,207); only the number
-// of consumed bits is observable, so the window width is free.  The payload buffer is padded so
-// that reads up to 16 bytes past any stream end are in bounds.
+// MSB-first bit reader over global memory.  Replaces update_buffer / INPUT_BITS
+// (LIB/decoder/lossless_decode.c:139-162,207); only the number of consumed bits is observable, so the
+// window mechanics are free: two consecutive big-endian 32-bit words (w0 = current, w1 = next) and a bit
+// offset into w0.  The next 32 stream bits are ONE funnel shift; consuming bits is an add, and when the
+// offset crosses a word the look-ahead word moves down and the following word is fetched -- a whole word
+// (3-4 symbols) before it is needed, which hides most of the load latency.  The payload buffer is padded
+// so that reads up to 16 bytes past any stream end are in bounds.
 // ------------------------------------------------------------------------------------------------
 struct BitReader {
-    const uint32_t* wp;    // next aligned word
-    uint64_t buf;          // next bit is bit 63
-    int nbits;             // valid bits in buf
+    const uint32_t* wp;    // next aligned word to fetch
+    uint32_t w0, w1;       // current and look-ahead word, MSB first
+    uint32_t off;          // consumed bits of w0, 0..31
 
+    __device__ static __forceinline__ const uint32_t* word_ptr(const uint8_t* base, uint32_t bitpos) {
+        return reinterpret_cast<const uint32_t*>((reinterpret_cast<uintptr_t>(base) + (bitpos >> 3)) & ~(uintptr_t)3);
+    }
     __device__ __forceinline__ void init(const uint8_t* base, uint32_t bitpos) {
         const uint32_t* p = word_ptr(base, bitpos);
         init_loaded(base, bitpos, __ldg(p), __ldg(p + 1));
     }
     // Two-step form: fetch word_ptr()[0..1] early (e.g. for several streams at once), start later.
-    __device__ static __forceinline__ const uint32_t* word_ptr(const uint8_t* base, uint32_t bitpos) {
-        return reinterpret_cast<const uint32_t*>((reinterpret_cast<uintptr_t>(base) + (bitpos >> 3)) & ~(uintptr_t)3);
-    }
     __device__ __forceinline__ void init_loaded(const uint8_t* base, uint32_t bitpos, uint32_t raw0, uint32_t raw1) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(base) + (bitpos >> 3);
-        const uint32_t skip = (uint32_t)(a & 3u) * 8u + (bitpos & 7u);
+        off = (uint32_t)(a & 3u) * 8u + (bitpos & 7u);
         wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3) + 2;
-        const uint32_t w0 = __byte_perm(raw0, 0, 0x0123), w1 = __byte_perm(raw1, 0, 0x0123);
-        buf = (((uint64_t)w0 << 32) | w1) << skip;
-        nbits = 64 - (int)skip;
+        w0 = __byte_perm(raw0, 0, 0x0123);
+        w1 = __byte_perm(raw1, 0, 0x0123);
     }
-    // Guarantees >= 32 valid bits (the longest symbol is 8 + 15 = 23 bits).
-    __device__ __forceinline__ void refill() {
-        if (nbits <= 32) {
-            uint32_t w = __byte_perm(__ldg(wp), 0, 0x0123);
+    __device__ __forceinline__ uint32_t top() const { return __funnelshift_l(w1, w0, off); }   // next 32 bits
+    __device__ __forceinline__ void skip(uint32_t n) {                                         // n <= 31
+        off += n;
+        if (off >= 32u) {
+            off -= 32u;
+            w0 = w1;
+            w1 = __byte_perm(__ldg(wp), 0, 0x0123);
             wp++;
-            buf |= (uint64_t)w << (32 - nbits);
-            nbits += 32;
         }
     }
-    __device__ __forceinline__ uint32_t top() const { return (uint32_t)(buf >> 32); }
-    __device__ __forceinline__ void skip(int n) { buf <<= n; nbits -= n; }
 };
 
-// JPEG VLI sign extension: HUFF_EXTEND, LIB/decoder/lossless_decode.c:204.  size in 1..15.
-__device__ __forceinline__ int vli_extend(uint32_t amp, int size) {
-    return (amp < (1u << (size - 1))) ? (int)amp - (1 << size) + 1 : (int)amp;
+// JPEG VLI sign extension: HUFF_EXTEND, LIB/decoder/lossless_decode.c:204.  size in 0..15; size 0 gives 0.
+// (amp < 2^(size-1) ? amp - 2^size + 1 : amp, written without the undefined shifts of the macro.)
+__device__ __forceinline__ int vli_extend(uint32_t amp, uint32_t size) {
+    const uint32_t full = 1u << size;
+    return (int)amp - ((amp < (full >> 1)) ? (int)(full - 1u) : 0);
+}
+// The `size` amplitude bits that follow a `hdr`-bit header in the 32-bit window t (0 for size 0).
+__device__ __forceinline__ uint32_t amp_bits(uint32_t t, uint32_t hdr, uint32_t size) {
+    return ((t << hdr) >> 1) >> (31u - size);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Symbol stepper shared by every segment-parallel pass (speculative parse, merge, chain re-parse,
 // block index) so that they all follow ONE trajectory function.  The passes run a single flat loop,
-// one symbol per iteration for every lane, with the DC/AC distinction and the block-end test
-// predicated -- lanes of a warp stay converged however their blocks are laid out.
+// one symbol per iteration for every lane; step() is branch-free (DC/AC and block-end handling are
+// selects), so the lanes of a warp stay converged however their blocks are laid out.
 //   DC symbol  input_DC  LIB/decoder/lossless_decode.c:210-224  (4-bit size + amplitude)
 //   AC symbol  input_AC  :227-246 (4-bit run, 4-bit size, amplitude); size 0: run 15 = ZRL else END
 //   block loop :101-133; `index` is uint8_t there and wraps, so it does here.
@@ -122,32 +129,23 @@ struct Parser {
     // Consume one symbol.  Returns true when it ended the block (the parser is then positioned on the
     // next block's DC symbol).  dc_e receives the DC amplitude when the symbol was a DC symbol, else 0.
     __device__ __forceinline__ bool step(uint32_t total_bits, int& dc_e) {
-        r.refill();
         const uint32_t t = r.top();
-        const uint32_t hdr = is_dc ? 4u : 8u;
+        const bool dc = is_dc;
+        const uint32_t hdr = dc ? 4u : 8u;
         const uint32_t rs = t >> (32u - hdr);
-        const uint32_t size = rs & 15u, run = rs >> 4;          // run is garbage-free: rs < 16 for a DC symbol
+        const uint32_t size = rs & 15u, run = rs >> 4;          // run == 0 for a DC symbol (rs < 16)
         const uint32_t len = hdr + size;
-        r.skip((int)len);
+        r.skip(len);
         pos += len;
-        bool end;
-        dc_e = 0;
-        if (is_dc) {
-            if (size) dc_e = vli_extend((t << 4) >> (32u - size), (int)size);
-            is_dc = false;
-            idx = 1;
-            end = false;
-        } else if (size == 0) {
-            end = run != 15u;                   // END (any run but 15) / ZRL
-            idx = (idx + 16u) & 255u;
-        } else {
-            idx = (idx + run) & 255u;
-            end = idx >= 63u;
-            idx++;
-        }
-        end |= (pos - blk_start) >= budget;
+        dc_e = dc ? vli_extend(amp_bits(t, 4u, size), size) : 0;
+        const bool coded = size != 0u && !dc;                   // a non-zero AC coefficient
+        const uint32_t adv = (dc ? 1u : idx) + (dc ? 0u : (size == 0u ? 16u : run));
+        const uint32_t at = adv & 255u;                         // DC: 1; ZRL: idx+16; coefficient: its zig-zag index
+        idx = at + (coded ? 1u : 0u);
+        bool end = (!dc && size == 0u && run != 15u) || (coded && at >= 63u);   // END symbol / coefficient 63
+        end = end || (pos - blk_start) >= budget;
+        is_dc = end;
         if (end) {
-            is_dc = true;
             blk_start = pos;
             budget = block_budget(pos, total_bits);
         }
@@ -183,30 +181,25 @@ __device__ __forceinline__ void parse_block_loaded(const uint8_t* base, uint32_t
     if (active) {
         r.init_loaded(base, bitpos, raw0, raw1);
         max_bits = block_budget(bitpos, total_bits);
-        r.refill();
         const uint32_t t = r.top();
         const uint32_t size = t >> 28;
-        int e = 0;
-        if (size) e = vli_extend((t << 4) >> (32u - size), (int)size);
-        r.skip((int)(4u + size));
+        r.skip(4u + size);
         used = 4u + size;
-        sink.dc(e);
+        sink.dc(vli_extend(amp_bits(t, 4u, size), size));
         active = used < max_bits;
     }
     while (__any_sync(FULL_MASK, active)) {
         if (active) {
-            r.refill();
             const uint32_t t = r.top();
             const uint32_t run = t >> 28, size = (t >> 24) & 15u;
-            r.skip((int)(8u + size));
+            r.skip(8u + size);
             used += 8u + size;
             if (size == 0) {
                 active = run == 15u;              // ZRL continues, END (any other run) stops
                 idx = (idx + 16u) & 255u;
             } else {
-                const int e = vli_extend((t << 8) >> (32u - size), (int)size);
                 idx = (idx + run) & 255u;
-                if (idx < 64u) sink.ac(idx, e);
+                if (idx < 64u) sink.ac(idx, vli_extend(amp_bits(t, 8u, size), size));
                 active = idx < 63u;
                 idx++;
             }
