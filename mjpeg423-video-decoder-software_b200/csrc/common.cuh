@@ -21,7 +21,10 @@ constexpr int ENT_TPB = 128;                   // threads per CTA in the entropy
 constexpr int MIN_BLOCK_BITS = 12;             // DC size 0 + END
 constexpr uint32_t RUNAWAY_BITS = 8192;        // parse guard for non-conforming / speculative garbage
 constexpr uint32_t MAX_STREAM_BYTES = 1u << 28; // bit positions are 32-bit
-constexpr uint32_t NO_BLOCK = 0xFFFFFFFFu;       // block index entry of a block the stream does not contain
+// Symbol list: the index pass writes every coded AC coefficient of a segment's blocks as one 32-bit entry
+// (zig-zag index | amplitude << 16) into a fixed-stride region.  A segment owns at most 2048/9 = 227 coded
+// symbols that start inside it plus the rest of its last block (a block has at most 63 AC coefficients).
+constexpr uint32_t SYM_STRIDE = 320;             // entries per segment (>= 227 + 63)
 
 // One plane bitstream of one frame (built by the host from the 16-byte frame headers,
 // LIB/decoder/mjpeg423_decoder.c:94-107).
@@ -126,9 +129,16 @@ struct Parser {
         idx = 1;
         is_dc = true;
     }
+    // What the last step() consumed.
+    struct Sym {
+        bool dc;           // it was the block's DC symbol
+        bool coded;        // it was a non-zero AC coefficient ...
+        uint32_t at;       // ... at this zig-zag index (may be >= 64 on non-conforming input: ignore then)
+        int e;             // amplitude of the DC / AC coefficient (0 for END and ZRL)
+    };
     // Consume one symbol.  Returns true when it ended the block (the parser is then positioned on the
-    // next block's DC symbol).  dc_e receives the DC amplitude when the symbol was a DC symbol, else 0.
-    __device__ __forceinline__ bool step(uint32_t total_bits, int& dc_e) {
+    // next block's DC symbol).
+    __device__ __forceinline__ bool step(uint32_t total_bits, Sym& sym) {
         const uint32_t t = r.top();
         const bool dc = is_dc;
         const uint32_t hdr = dc ? 4u : 8u;
@@ -137,7 +147,6 @@ struct Parser {
         const uint32_t len = hdr + size;
         r.skip(len);
         pos += len;
-        dc_e = dc ? vli_extend(amp_bits(t, 4u, size), size) : 0;
         const bool coded = size != 0u && !dc;                   // a non-zero AC coefficient
         const uint32_t adv = (dc ? 1u : idx) + (dc ? 0u : (size == 0u ? 16u : run));
         const uint32_t at = adv & 255u;                         // DC: 1; ZRL: idx+16; coefficient: its zig-zag index
@@ -149,64 +158,22 @@ struct Parser {
             blk_start = pos;
             budget = block_budget(pos, total_bits);
         }
+        sym.dc = dc;
+        sym.coded = coded;
+        sym.at = at;
+        sym.e = vli_extend(amp_bits(t, hdr, size), size);
+        return end;
+    }
+    // Parse-only form: dc_e receives the DC amplitude when the symbol was a DC symbol, else 0.
+    __device__ __forceinline__ bool step(uint32_t total_bits, int& dc_e) {
+        Sym sym;
+        const bool end = step(total_bits, sym);
+        dc_e = sym.dc ? sym.e : 0;
         return end;
     }
 };
 
-// ------------------------------------------------------------------------------------------------
-// Single-block parser for the block-parallel decode kernels: the same trajectory function as
-// Parser::step, restricted to one block, delivering coefficients to a sink.
-// Sink::dc(e) / Sink::ac(zigzag_index, e).
-// WARP-COLLECTIVE: all 32 lanes must call it (lanes without a block pass active = false).  The symbol
-// loop runs under a warp vote so that the lanes re-converge every iteration; with independent thread
-// scheduling a plain data-dependent loop lets the warp fragment for good (profiles/r01b: 7 of 32 lanes
-// active per instruction).
-// ------------------------------------------------------------------------------------------------
 constexpr uint32_t FULL_MASK = 0xFFFFFFFFu;
-
-template <class Sink>
-__device__ __forceinline__ void parse_block_loaded(const uint8_t* base, uint32_t bitpos, uint32_t total_bits, Sink& sink,
-                                                   bool active, uint32_t raw0, uint32_t raw1);
-template <class Sink>
-__device__ __forceinline__ void parse_block(const uint8_t* base, uint32_t bitpos, uint32_t total_bits, Sink& sink,
-                                            bool active) {
-    const uint32_t* p0 = BitReader::word_ptr(base, active ? bitpos : 0u);
-    parse_block_loaded(base, bitpos, total_bits, sink, active, active ? __ldg(p0) : 0u, active ? __ldg(p0 + 1) : 0u);
-}
-template <class Sink>
-__device__ __forceinline__ void parse_block_loaded(const uint8_t* base, uint32_t bitpos, uint32_t total_bits, Sink& sink,
-                                                   bool active, uint32_t raw0, uint32_t raw1) {
-    BitReader r;
-    uint32_t max_bits = 0, used = 0, idx = 1;
-    if (active) {
-        r.init_loaded(base, bitpos, raw0, raw1);
-        max_bits = block_budget(bitpos, total_bits);
-        const uint32_t t = r.top();
-        const uint32_t size = t >> 28;
-        r.skip(4u + size);
-        used = 4u + size;
-        sink.dc(vli_extend(amp_bits(t, 4u, size), size));
-        active = used < max_bits;
-    }
-    while (__any_sync(FULL_MASK, active)) {
-        if (active) {
-            const uint32_t t = r.top();
-            const uint32_t run = t >> 28, size = (t >> 24) & 15u;
-            r.skip(8u + size);
-            used += 8u + size;
-            if (size == 0) {
-                active = run == 15u;              // ZRL continues, END (any other run) stops
-                idx = (idx + 16u) & 255u;
-            } else {
-                idx = (idx + run) & 255u;
-                if (idx < 64u) sink.ac(idx, vli_extend(amp_bits(t, 8u, size), size));
-                active = idx < 63u;
-                idx++;
-            }
-            active = active && used < max_bits;
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // 8-point LL&M inverse DCT pass: LIB/decoder/idct.c:46-97 (pass 1) == :123-168 (pass 2).

@@ -1,18 +1,20 @@
 // decode.cu -- block-parallel final decode (sm_100a): one thread per 8x8 block.
 //
-// After entropy.cu has produced the block index (bit position of every block's DC symbol + absolute DC
-// level), every block of every plane can be decoded independently:
+// After entropy.cu has produced the symbol lists and the block index (list position, entry count and
+// absolute DC level of every block), every block of every plane can be decoded independently and
+// without any bit-serial work:
 //
-//   k_decode_coef   lossless_decode() output, LIB/decoder/lossless_decode.c:60-135: the thread parses its
-//                   block into a 128-byte shared-memory slot (zeroed = the memset of :77-78, or preloaded
+//   k_decode_coef   lossless_decode() output, LIB/decoder/lossless_decode.c:60-135: the thread scatters its
+//                   block's entries into a 128-byte shared-memory slot (zeroed = the memset of :77-78, or preloaded
 //                   with the previous frame's coefficients for P frames, :90-92,121-123), dequantising
 //                   as it scatters zig-zag -> natural order (:122-126); the CTA then stores its 128
 //                   consecutive blocks as one contiguous, fully coalesced 16 KB run.
 //   k_decode_fused  the whole reference loop body, LIB/decoder/mjpeg423_decoder.c:110-124, for intra
-//                   frames: the thread parses the Y, Cb and Cr block of one block position through the
+//                   frames: the thread scatters the Y, Cb and Cr block of one block position through the
 //                   same slot, runs the three IDCTs in registers (idct.c:22-181) and writes the 8x8
 //                   BGRA pixels (ycbcr_to_rgb.c:26-49).  Coefficients and samples never touch HBM:
-//                   the kernel reads C + 6 bytes of index per block and writes 4 bytes per pixel.
+//                   the kernel reads the lists (4 bytes per coded coefficient + 8 per block) and writes
+//                   4 bytes per pixel.
 // (LIB = /root/reference/core0/software/common/libs/mjpeg423.)
 //
 // Slots use the XOR swizzle of idct_colour.cu (16-byte chunk r of slot t at chunk r ^ (t & 7)), so both
@@ -34,35 +36,6 @@ __device__ __forceinline__ uint32_t slot_off(int t, uint32_t n) {
     return (uint32_t)t * 128u + ((((n >> 3) ^ (uint32_t)t) & 7u) << 4) + ((n & 7u) << 1);
 }
 
-// Sink of parse_block(): dequantise and scatter into the slot, tracking column occupancy for the IDCT.
-template <bool PFRAME>
-struct SlotSink {
-    uint8_t* smem;              // slot array
-    const uint32_t* zq;         // smem: natural index | quant << 16, by zig-zag position
-    int t;
-    int cur;                    // I frames: absolute DC level from the block index
-    uint32_t m_ac, m_any;       // column masks (see block_masks() in common.cuh)
-    __device__ __forceinline__ int16_t& at(uint32_t n) { return *reinterpret_cast<int16_t*>(smem + slot_off(t, n)); }
-    __device__ __forceinline__ void dc(int e) {
-        const int q0 = (int)(zq[0] >> 16);
-        int16_t& d = at(0);
-        if (PFRAME) d = (int16_t)(d + e * q0);                     // lossless_decode.c:91
-        else d = (int16_t)((int)(int16_t)cur * q0);                // :94-95 (cur already includes e)
-        m_any |= 1u;
-    }
-    __device__ __forceinline__ void ac_(uint32_t n, int v) {
-        int16_t& d = at(n);
-        if (PFRAME) d = (int16_t)(d + v);                          // :122
-        else d = (int16_t)v;                                       // :125
-        m_any |= 1u << (n & 7u);
-        if (n >= 8u) m_ac |= 1u << (n & 7u);
-    }
-    __device__ __forceinline__ void ac(uint32_t idx, int e) {     // never called with idx >= 64
-        const uint32_t z = zq[idx];
-        ac_(z & 0xFFFFu, e * (int)(z >> 16));
-    }
-};
-
 __device__ __forceinline__ void load_zq(uint32_t* s_zq, const int16_t* quant, int t) {
     if (t < 64) {
         const uint32_t n = c_zigzag[t];
@@ -81,9 +54,8 @@ __device__ __forceinline__ void load_slot_rows(const uint8_t* smem, int t, uint4
 // ---- coefficient planes ------------------------------------------------------------------------------
 // grid = (ceil(nb / 128), number of streams in `stream_ids`).
 __global__ void __launch_bounds__(DEC_TPB)
-k_decode_coef(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
-              const uint32_t* __restrict__ stream_ids, const uint32_t* __restrict__ blk_pos,
-              const int16_t* __restrict__ blk_dc, const int16_t* __restrict__ quant, int16_t* coef) {
+k_decode_coef(const StreamDesc* __restrict__ streams, const uint32_t* __restrict__ stream_ids,
+              const uint2* __restrict__ blk_info, const uint32_t* __restrict__ sym, const int16_t* __restrict__ quant, int16_t* coef) {
     __shared__ __align__(128) uint8_t slots[DEC_TPB * 128];
     __shared__ uint32_t s_zq[64];
     const int t = threadIdx.x;
@@ -104,17 +76,24 @@ k_decode_coef(const uint8_t* __restrict__ payload, const StreamDesc* __restrict_
         zero_slot(slots, t);
     }
     __syncthreads();
-    {
+    if ((uint32_t)t < nblk) {
         const uint32_t gb = sd.block_base + b0 + (uint32_t)t;
-        const bool have = (uint32_t)t < nblk;
-        const uint32_t pos = have ? blk_pos[gb] : NO_BLOCK;
-        const uint8_t* base = payload + sd.byte_off;
-        if (sd.ptype) {
-            SlotSink<true> sink{slots, s_zq, t, 0, 0, 0};
-            parse_block(base, pos, sd.byte_len * 8u, sink, pos != NO_BLOCK);
-        } else {
-            SlotSink<false> sink{slots, s_zq, t, have ? (int)blk_dc[gb] : 0, 0, 0};
-            parse_block(base, pos, sd.byte_len * 8u, sink, pos != NO_BLOCK);
+        const uint2 info = __ldg(blk_info + gb);
+        const uint32_t meta = info.y;
+        const uint32_t* src = sym + info.x;
+        const uint32_t n = meta >> 16;
+        const int dc = (int)(int16_t)(meta & 0xFFFFu);
+        int16_t* d0 = reinterpret_cast<int16_t*>(slots + slot_off(t, 0));
+        const int q0 = (int)(s_zq[0] >> 16);
+        if (sd.ptype) *d0 = (int16_t)(*d0 + dc * q0);                    // lossless_decode.c:91 (dc = the delta)
+        else *d0 = (int16_t)(dc * q0);                                   // :94-95 (dc = running sum `cur`)
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t ent = __ldg(src + i);
+            const uint32_t z = s_zq[ent & 63u];
+            int16_t* d = reinterpret_cast<int16_t*>(slots + slot_off(t, z & 0xFFFFu));
+            const int v = ((int)ent >> 16) * (int)(z >> 16);
+            if (sd.ptype) *d = (int16_t)(*d + v);                        // :122
+            else *d = (int16_t)v;                                        // :125
         }
     }
     __syncthreads();
@@ -142,28 +121,9 @@ k_decode_coef(const uint8_t* __restrict__ payload, const StreamDesc* __restrict_
 constexpr int FUSED_TPB = 448;                                   // 14 warps x 512 B/thread = 224 KB of the SM's 227 KB
 constexpr int FUSED_SMEM = FUSED_TPB * (128 + 256 + 128) + 2 * 64 * 4;
 
-struct FusedSink {              // parse_block() sink: dequantise, scatter transposed, track occupancy
-    uint8_t* coef;              // this thread's base: coef + t*16
-    const uint32_t* zq;         // smem: transposed byte offset | quant << 16, by zig-zag position
-    int cur;
-    uint32_t m_ac, m_any;
-    __device__ __forceinline__ void dc(int) {
-        *reinterpret_cast<int16_t*>(coef) = (int16_t)((int)(int16_t)cur * (int)(zq[0] >> 16));   // lossless_decode.c:94-95
-        m_any |= 1u;
-    }
-    __device__ __forceinline__ void ac(uint32_t idx, int e) {
-        const uint32_t z = zq[idx];
-        const uint32_t off = z & 0xFFFFu;                       // column * (T*16) + row * 2
-        *reinterpret_cast<int16_t*>(coef + off) = (int16_t)(e * (int)(z >> 16));              // :125
-        const uint32_t col = off / (FUSED_TPB * 16u);
-        m_any |= 1u << col;
-        if (off & 15u) m_ac |= 1u << col;                       // row >= 1
-    }
-};
-
 __global__ void __launch_bounds__(FUSED_TPB, 1)
-k_decode_fused(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
-               const uint32_t* __restrict__ blk_pos, const int16_t* __restrict__ blk_dc,
+k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__ blk_info,
+               const uint32_t* __restrict__ sym,
                const int16_t* __restrict__ quant, uint8_t* __restrict__ out, uint32_t nb, uint32_t wb, uint32_t W,
                uint32_t n_frames) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -190,36 +150,47 @@ k_decode_fused(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
         const StreamDesc* sd0 = streams + (size_t)f * 3;
         uint8_t* dst = out + ((size_t)f * nb * 64 + ((size_t)(b / wb) * 8 * W + (size_t)(b % wb) * 8)) * 4;
 
-        // Fetch the index entries and the first two bitstream words of all three planes up front: the
-        // three dependent global round trips overlap instead of serialising in front of each parse.
-        uint32_t pos[3], raw0[3], raw1[3];
-        int dcl[3];
+        // Fetch the index entries of all three planes up front (independent, coalesced loads).
+        uint32_t off[3], meta[3];
 #pragma unroll
         for (int p = 0; p < 3; p++) {
             const uint32_t gb = sd0[p].block_base + b;
-            pos[p] = live ? blk_pos[gb] : NO_BLOCK;
-            dcl[p] = live ? (int)blk_dc[gb] : 0;
-        }
-#pragma unroll
-        for (int p = 0; p < 3; p++) {
-            const bool have = pos[p] != NO_BLOCK;
-            const uint32_t* wp = BitReader::word_ptr(payload + sd0[p].byte_off, have ? pos[p] : 0u);
-            raw0[p] = have ? __ldg(wp) : 0u;
-            raw1[p] = have ? __ldg(wp + 1) : 0u;
+            const uint2 info = live ? __ldg(blk_info + gb) : make_uint2(0u, 0u);
+            off[p] = info.x;
+            meta[p] = info.y;
         }
 
 #pragma unroll 1
         for (int p = 0; p < 3; p++) {
-            // ---- parse this plane's block into the (zeroed) transposed coefficient slot -------------------
+            // ---- scatter this plane's block into the (zeroed) transposed coefficient slot -----------------
 #pragma unroll
             for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(my_coef + c * (FUSED_TPB * 16)) = make_uint4(0, 0, 0, 0);
             // (p is a loop variable: select the pre-fetched registers without dynamic indexing)
-            const uint32_t ppos = p == 0 ? pos[0] : p == 1 ? pos[1] : pos[2];
-            const uint32_t pr0 = p == 0 ? raw0[0] : p == 1 ? raw0[1] : raw0[2];
-            const uint32_t pr1 = p == 0 ? raw1[0] : p == 1 ? raw1[1] : raw1[2];
-            FusedSink sink{my_coef, s_zq + (p ? 64 : 0), p == 0 ? dcl[0] : p == 1 ? dcl[1] : dcl[2], 0, 0};
-            parse_block_loaded(payload + sd0[p].byte_off, ppos, sd0[p].byte_len * 8u, sink, ppos != NO_BLOCK, pr0, pr1);
-            const uint32_t acm = warp_or(sink.m_ac), anym = warp_or(sink.m_any);    // warp-uniform from here on
+            const uint32_t pmeta = p == 0 ? meta[0] : p == 1 ? meta[1] : meta[2];
+            const uint32_t* src = sym + (p == 0 ? off[0] : p == 1 ? off[1] : off[2]);
+            const uint32_t* zq = s_zq + (p ? 64 : 0);
+            const uint32_t n = pmeta >> 16;
+            *reinterpret_cast<int16_t*>(my_coef) = (int16_t)((int)(int16_t)(pmeta & 0xFFFFu) * (int)(zq[0] >> 16));  // lossless_decode.c:94-95
+            uint32_t m_ac = 0, m_any = 1u;
+            const uint32_t nmax = __reduce_max_sync(FULL_MASK, n);        // warp-uniform trip count
+            for (uint32_t i = 0; i < nmax; i += 2) {                      // two independent loads in flight
+                const uint32_t e0 = i < n ? __ldg(src + i) : 0u;
+                const uint32_t e1 = i + 1 < n ? __ldg(src + i + 1) : 0u;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t ent = h ? e1 : e0;
+                    if (i + h < n) {
+                        const uint32_t z = zq[ent & 63u];
+                        const uint32_t o = z & 0xFFFFu;                   // column * (T*16) + row * 2
+                        *reinterpret_cast<int16_t*>(my_coef + o) = (int16_t)(((int)ent >> 16) * (int)(z >> 16));   // :125
+                        const uint32_t col = o / (FUSED_TPB * 16u);
+                        m_any |= 1u << col;
+                        if (o & 15u) m_ac |= 1u << col;                   // row >= 1
+                    }
+                }
+            }
+            __syncwarp();
+            const uint32_t acm = warp_or(m_ac), anym = warp_or(m_any);    // warp-uniform from here on
 
             // emit(r, w0, w1): Y and Cb rows go to the stash, a Cr row completes 8 pixels.
             auto emit = [&](int r, uint32_t w0, uint32_t w1) {
@@ -283,7 +254,7 @@ cudaError_t launch_decode_coef(const EntropyJob& j, const uint32_t* d_stream_ids
                                const int16_t* d_quant, int16_t* d_coef, cudaStream_t s) {
     if (n_ids == 0 || nb == 0) return cudaSuccess;
     dim3 grid((nb + DEC_TPB - 1) / DEC_TPB, n_ids);
-    k_decode_coef<<<grid, DEC_TPB, 0, s>>>(j.d_payload, j.d_streams, d_stream_ids, j.d_blk_pos, j.d_blk_dc, d_quant, d_coef);
+    k_decode_coef<<<grid, DEC_TPB, 0, s>>>(j.d_streams, d_stream_ids, j.d_blk_info, j.d_sym, d_quant, d_coef);
     return cudaGetLastError();
 }
 cudaError_t launch_decode_fused(const EntropyJob& j, const int16_t* d_quant, void* d_out, uint32_t n_frames,
@@ -301,7 +272,7 @@ cudaError_t launch_decode_fused(const EntropyJob& j, const int16_t* d_quant, voi
     const uint64_t n_tiles = (uint64_t)((nb + 31) / 32) * n_frames;
     const uint64_t want = (n_tiles + FUSED_TPB / 32 - 1) / (FUSED_TPB / 32);
     const unsigned grid = (unsigned)(want < (uint64_t)n_sm ? want : (uint64_t)n_sm);     // persistent: one CTA per SM
-    k_decode_fused<<<grid, FUSED_TPB, FUSED_SMEM, s>>>(j.d_payload, j.d_streams + j.stream_lo, j.d_blk_pos, j.d_blk_dc,
+    k_decode_fused<<<grid, FUSED_TPB, FUSED_SMEM, s>>>(j.d_streams + j.stream_lo, j.d_blk_info, j.d_sym,
                                                        d_quant, (uint8_t*)d_out, nb, wb, W, n_frames);
     return cudaGetLastError();
 }

@@ -16,9 +16,10 @@
 //                    entry[0] = 0 (correctness never rests on self-synchronisation, only speed does),
 //                    then exclusive-scans block counts and DC sums (mod 2^16) to
 //                    give every segment its first block index and DC predictor.
-//   k_entropy_index  one thread per segment walks its blocks from the now exact state and writes, per
-//                    block, the bit position of its DC symbol and the absolute DC level: the index the
-//                    block-parallel decode kernels (decode.cu) start from.
+//   k_entropy_index  one thread per segment walks its blocks from the now exact state and writes every
+//                    coded coefficient as a 32-bit entry into the segment's symbol list, plus per block
+//                    the list position, entry count and absolute DC level: what the block-parallel
+//                    decode kernels (decode.cu) consume without touching the bitstream again.
 //
 // Every pass advances with Parser::step() (common.cuh): one flat loop, one symbol per iteration per
 // lane, DC/AC and block-end handling predicated, so the lanes of a warp stay converged.
@@ -256,14 +257,19 @@ k_entropy_chain(const uint8_t* __restrict__ payload, const StreamDesc* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// Block index: per block, the bit position of its DC symbol and its absolute DC level
-// (`cur` of LIB/decoder/lossless_decode.c:73,94 -- the running sum of DC deltas, int16).
+// Block index + symbol lists.  Walking its blocks from the exact state, a segment's thread writes
+//   sym[seg * SYM_STRIDE + ...]  one entry per coded AC coefficient: zig-zag index | amplitude << 16
+//   blk_info[block].x            index of the block's first entry in sym[]
+//   blk_info[block].y            absolute DC level (`cur` of LIB/decoder/lossless_decode.c:73,94, the int16
+//                                running sum of DC deltas; for P frames the DC delta itself, :91) | entries << 16
+// After this pass no kernel touches the bitstream again: the block-parallel decode kernels (decode.cu)
+// read the lists with independent, look-ahead loads instead of a bit-serial dependent chain.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ENT_TPB)
 k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
                 const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ seg_entry,
                 const uint32_t* __restrict__ seg_cd, const uint32_t* __restrict__ seg_first,
-                uint32_t* __restrict__ blk_pos, int16_t* __restrict__ blk_dc) {
+                uint2* __restrict__ blk_info, uint32_t* __restrict__ sym, uint32_t sym_seg0) {
     const int t = threadIdx.x;
     const TileDesc td = tiles[blockIdx.x];
     const StreamDesc sd = streams[td.stream];
@@ -276,26 +282,41 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
     const uint32_t cd = valid ? seg_cd[g] : 0u;
     uint32_t cnt = cd & 0xFFFFu;
     cnt = first >= sd.nb ? 0u : min(cnt, sd.nb - first);          // trailing pad bits can look like blocks
-    uint32_t* bp = blk_pos + sd.block_base + first;
-    int16_t* bd = blk_dc + sd.block_base + first;
+    uint2* bi = blk_info + sd.block_base + first;
+    const uint32_t o_base = (g - sym_seg0) * SYM_STRIDE, o_end = o_base + SYM_STRIDE;   // chunk-relative entry index
+    uint32_t o = o_base, o_blk = o_base;
     bool active = valid && cnt != 0;
     Parser ps;
     if (active) ps.start(base, seg_entry[g], total_bits);
-    int cur = (int)(cd >> 16);
+    int cur = sd.ptype ? 0 : (int)(cd >> 16);
+    const bool pframe = sd.ptype != 0;
     uint32_t k = 0;
+    uint4 q = make_uint4(0, 0, 0, 0);          // the last (o & 3) entries, oldest in .x: stored 16 bytes at a time
     while (__any_sync(FULL_MASK, active)) {
         if (active) {
-            const bool was_dc = ps.is_dc;
-            const uint32_t at = ps.pos;
-            int e;
-            const bool end = ps.step(total_bits, e);
-            if (was_dc) { cur += e; bp[k] = at; bd[k] = (int16_t)cur; }
-            if (end && ++k == cnt) active = false;
+            Parser::Sym y;
+            const bool end = ps.step(total_bits, y);
+            if (y.dc) { cur = pframe ? y.e : cur + y.e; o_blk = o; }
+            if (y.coded && y.at < 64u) {
+                q.x = q.y; q.y = q.z; q.z = q.w; q.w = y.at | ((uint32_t)y.e << 16);
+                o++;
+                if ((o & 3u) == 0u && o <= o_end)                        // never overflows on conforming streams
+                    *reinterpret_cast<uint4*>(sym + o - 4) = q;
+            }
+            if (end) {
+                bi[k] = make_uint2(o_blk, ((uint32_t)cur & 0xFFFFu) | ((min(o, o_end) - min(o_blk, o_end)) << 16));
+                if (++k == cnt) active = false;
+            }
         }
+    }
+    if (valid && (o & 3u) && o < o_end) {      // flush the partial group (entries beyond o are never read)
+        const uint32_t r = o & 3u;
+        const uint4 v = r == 1 ? make_uint4(q.w, 0, 0, 0) : r == 2 ? make_uint4(q.z, q.w, 0, 0) : make_uint4(q.y, q.z, q.w, 0);
+        *reinterpret_cast<uint4*>(sym + (o & ~3u)) = v;
     }
     // A stream that ends early leaves the remaining blocks empty (zero coefficients).
     if (valid && seg + 1 == sd.nseg)
-        for (uint32_t b = first + cnt; b < sd.nb; b++) { blk_pos[sd.block_base + b] = NO_BLOCK; blk_dc[sd.block_base + b] = 0; }
+        for (uint32_t b = first + cnt; b < sd.nb; b++) blk_info[sd.block_base + b] = make_uint2(0, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -317,7 +338,7 @@ cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s) {
 cudaError_t launch_entropy_index(const EntropyJob& j, cudaStream_t s) {
     if (j.n_write_tiles == 0) return cudaSuccess;
     k_entropy_index<<<j.n_write_tiles, ENT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_write_tiles, j.d_seg_entry,
-                                                        j.d_seg_cd, j.d_seg_first, j.d_blk_pos, j.d_blk_dc);
+                                                        j.d_seg_cd, j.d_seg_first, j.d_blk_info, j.d_sym, j.sym_seg0);
     return cudaGetLastError();
 }
 

@@ -337,11 +337,21 @@ int decode_mode(const mjpeg423_b200_ctx* c, const Plan& plan) {
     return plan.n_pframes ? std::max(1, c->staged) : c->staged;     // P frames need coefficient state in HBM
 }
 
-// Per-chunk scratch: block index (6 bytes per block) and, in the staged modes, coefficient planes.
-int reserve_chunk_buffers(mjpeg423_b200_ctx* c, const Plan& plan, uint32_t frames, int nbuf) {
-    const size_t blocks = (size_t)frames * 3 * plan.nb;
+// Per-chunk scratch: block index (8 bytes per block) + symbol lists (SYM_STRIDE entries per segment) and,
+// in the staged modes, coefficient planes.
+size_t chunk_index_bytes(const Plan& plan, uint32_t f0, uint32_t f1) {
+    const size_t blocks = (size_t)(f1 - f0) * 3 * plan.nb, segs = plan.f_seg0[f1] - plan.f_seg0[f0];
+    return blocks * 8 + segs * (size_t)SYM_STRIDE * 4 + 256;
+}
+int reserve_chunk_buffers(mjpeg423_b200_ctx* c, const Plan& plan, const std::vector<Chunk>& chunks, int nbuf) {
+    size_t idx_bytes = 0, frames = 0;
+    for (const Chunk& ch : chunks) {
+        idx_bytes = std::max(idx_bytes, chunk_index_bytes(plan, ch.f0, ch.f1));
+        frames = std::max<size_t>(frames, ch.f1 - ch.f0);
+    }
+    const size_t blocks = frames * 3 * plan.nb;
     for (int i = 0; i < nbuf; i++) {
-        int rc = c->blkidx[i].reserve(blocks * 6 + 256);
+        int rc = c->blkidx[i].reserve(idx_bytes);
         if (rc) return rc;
         if (decode_mode(c, plan) && (rc = c->coef[i].reserve(blocks * 128))) return rc;
     }
@@ -362,9 +372,12 @@ EntropyJob make_job(const Plan& plan, const Tables& t, const uint8_t* d_payload_
     j.d_seg_entry = t.seg_entry; j.d_seg_exit = t.seg_exit; j.d_seg_cd = t.seg_cd; j.d_seg_first = t.seg_first;
     j.d_stream_blocks = t.stream_blocks; j.d_fixups = t.fixups;
     // StreamDesc.block_base is plan-relative: shift the chunk buffers back by the chunk's first block
+    // ... and StreamDesc.seg_base too: same for the symbol lists
     const size_t blocks = (size_t)(f1 - f0) * 3 * plan.nb, first_block = (size_t)f0 * 3 * plan.nb;
-    j.d_blk_pos = static_cast<uint32_t*>(d_blkidx) - first_block;
-    j.d_blk_dc = reinterpret_cast<int16_t*>(static_cast<uint32_t*>(d_blkidx) + blocks) - first_block;
+    uint32_t* w = static_cast<uint32_t*>(d_blkidx);
+    j.d_blk_info = reinterpret_cast<uint2*>(w) - first_block;
+    j.d_sym = w + ((2 * blocks + 3) & ~(size_t)3);   // 16-byte aligned; entries are relative to the chunk's first segment
+    j.sym_seg0 = plan.f_seg0[f0];
     return j;
 }
 
@@ -485,12 +498,13 @@ extern "C" int mjpeg423_b200_decode_resident(mjpeg423_b200_ctx* c, void* d_out) 
     if (!d_out) return MJPEG423_E_ARG;
     Tables t = tables_of(c, plan);
     // chunk size: bounded scratch (block index 6 B/block, + 128 B/block of coefficients in the staged modes)
-    const size_t scratch_frame = (size_t)3 * plan.nb * (decode_mode(c, plan) ? 134 : 6);
+    const size_t scratch_frame = (size_t)3 * plan.nb * (decode_mode(c, plan) ? 136 : 8) +
+                                 (size_t)(plan.f_seg0.back() / plan.n + 1) * SYM_STRIDE * 4;
     const uint32_t K = c->chunk_frames ? std::min(c->chunk_frames, plan.n) : auto_chunk(plan, (uint64_t)3 << 30, scratch_frame);
     int rc = prepare_chunks(c, plan, K, c->s_compute);
     if (rc) return rc;
     const int nbuf = (c->chunks.size() > 1 && !c->profile) ? 2 : 1;
-    if ((rc = reserve_chunk_buffers(c, plan, max_chunk_frames(c->chunks), nbuf))) return rc;
+    if ((rc = reserve_chunk_buffers(c, plan, c->chunks, nbuf))) return rc;
     cudaStream_t st[2] = {c->s_compute, c->s_aux};
     cudaEvent_t ev_start = c->ev[0], ev_stop = c->ev[1], ev_fork = c->ev[2], ev_join = c->ev[3];
     cudaEvent_t* prof = c->profile ? &c->ev[4] : nullptr;
@@ -532,7 +546,7 @@ extern "C" int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* c, int16_t* d_c
     cudaStream_t s = c->s_compute;
     int rc = prepare_chunks(c, plan, plan.n, s);          // one chunk: the caller's buffer holds every frame
     if (rc) return rc;
-    if ((rc = c->blkidx[0].reserve((size_t)plan.n * 3 * plan.nb * 6 + 256))) return rc;
+    if ((rc = c->blkidx[0].reserve(chunk_index_bytes(plan, 0, plan.n)))) return rc;
     const Chunk& ch = c->chunks[0];
     EntropyJob j = make_job(plan, t, c->payload.as<uint8_t>(), 0, plan.n, c->blkidx[0].p);
     cudaEvent_t* e = &c->ev[4];
@@ -617,7 +631,7 @@ extern "C" int mjpeg423_b200_decode_frames(mjpeg423_b200_ctx* c, const uint8_t* 
     const uint32_t K = c->chunk_frames ? std::min(c->chunk_frames, n) : auto_chunk(plan, (uint64_t)512 << 20, frame_bytes);
     if ((rc = prepare_chunks(c, plan, K, c->s_in))) return rc;
     const uint32_t maxf = max_chunk_frames(c->chunks);
-    if ((rc = reserve_chunk_buffers(c, plan, maxf, 1))) return rc;
+    if ((rc = reserve_chunk_buffers(c, plan, c->chunks, 1))) return rc;
     size_t max_in = 0;                                      // largest compressed chunk
     for (const Chunk& ch : c->chunks)
         max_in = std::max<size_t>(max_in, plan.frames[ch.f1 - 1].off + plan.frames[ch.f1 - 1].size - plan.frames[ch.f0].off);

@@ -25,8 +25,9 @@ struct EntropyJob {
     uint32_t *d_seg_entry = nullptr, *d_seg_exit = nullptr, *d_seg_cd = nullptr, *d_seg_first = nullptr; // plan-wide
     uint32_t* d_stream_blocks = nullptr;         // plan-wide, per stream
     unsigned long long* d_fixups = nullptr;
-    uint32_t* d_blk_pos = nullptr;               // block index, addressed by StreamDesc.block_base + b
-    int16_t* d_blk_dc = nullptr;
+    uint2* d_blk_info = nullptr;                 // block index, addressed by StreamDesc.block_base + b
+    uint32_t* d_sym = nullptr;                   // symbol lists: segment g's region starts at (g - sym_seg0) * SYM_STRIDE
+    uint32_t sym_seg0 = 0;
 };
 
 cudaError_t launch_entropy_sync(const EntropyJob& j, cudaStream_t s);
