@@ -65,7 +65,7 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     if ((rc = s_in.reserve(len + 64))) return rc;
     if ((rc = s_tab.reserve(256 + 256 + b_sync + b_write))) return rc;
     if ((rc = s_seg.reserve((size_t)sd.nseg * 16 + 64))) return rc;
-    if ((rc = s_idx.reserve((size_t)num_blocks * 8 + (size_t)sd.nseg * SYM_STRIDE * 4 + 64))) return rc;
+    if ((rc = s_idx.reserve((size_t)num_blocks * 8 + (size_t)sd.nseg * SYM_STRIDE * 4 + 128))) return rc;
     if ((rc = s_mid.reserve(coef_bytes))) return rc;
     uint8_t* tab = s_tab.as<uint8_t>();
     int16_t* d_q = reinterpret_cast<int16_t*>(tab);                  // 128 int16 (table 0 used)
@@ -90,7 +90,7 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     j.d_stream_blocks = seg + 4 * (size_t)sd.nseg;
     j.d_fixups = reinterpret_cast<unsigned long long*>(seg + 4 * (size_t)sd.nseg + 2);
     j.d_blk_info = s_idx.as<uint2>();
-    j.d_sym = s_idx.as<uint32_t>() + ((2 * (size_t)num_blocks + 3) & ~(size_t)3);
+    j.d_sym = s_idx.as<uint32_t>() + ((2 * (size_t)num_blocks + 7) & ~(size_t)7);
     j.sym_seg0 = 0;
     uint32_t* d_ids = reinterpret_cast<uint32_t*>(tab + 256 + 128);     // one id: stream 0
     CUX(cudaMemsetAsync(d_ids, 0, 4, s));

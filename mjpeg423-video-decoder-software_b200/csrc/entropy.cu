@@ -291,17 +291,19 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
     int cur = sd.ptype ? 0 : (int)(cd >> 16);
     const bool pframe = sd.ptype != 0;
     uint32_t k = 0;
-    uint4 q = make_uint4(0, 0, 0, 0);          // the last (o & 3) entries, oldest in .x: stored 16 bytes at a time
+    uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // the last (o & 7) entries, newest in q[7]: stored one full 32-byte
+                                               // sector at a time (a partial-sector store makes L2 fetch the rest)
     while (__any_sync(FULL_MASK, active)) {
         if (active) {
             Parser::Sym y;
             const bool end = ps.step(total_bits, y);
             if (y.dc) { cur = pframe ? y.e : cur + y.e; o_blk = o; }
             if (y.coded && y.at < 64u) {
-                q.x = q.y; q.y = q.z; q.z = q.w; q.w = y.at | ((uint32_t)y.e << 16);
+#pragma unroll
+                for (int i = 0; i < 7; i++) q[i] = q[i + 1];
+                q[7] = y.at | ((uint32_t)y.e << 16);
                 o++;
-                if ((o & 3u) == 0u && o <= o_end)                        // never overflows on conforming streams
-                    *reinterpret_cast<uint4*>(sym + o - 4) = q;
+                if ((o & 7u) == 0u && o <= o_end) st_global_v8(sym + o - 8, q);   // never overflows on conforming streams
             }
             if (end) {
                 bi[k] = make_uint2(o_blk, ((uint32_t)cur & 0xFFFFu) | ((min(o, o_end) - min(o_blk, o_end)) << 16));
@@ -309,10 +311,17 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
             }
         }
     }
-    if (valid && (o & 3u) && o < o_end) {      // flush the partial group (entries beyond o are never read)
-        const uint32_t r = o & 3u;
-        const uint4 v = r == 1 ? make_uint4(q.w, 0, 0, 0) : r == 2 ? make_uint4(q.z, q.w, 0, 0) : make_uint4(q.y, q.z, q.w, 0);
-        *reinterpret_cast<uint4*>(sym + (o & ~3u)) = v;
+    if (valid && (o & 7u) && o < o_end) {      // flush the partial group (entries beyond o are never read)
+        const uint32_t r = o & 7u;
+        uint32_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {          // v[i] = q[8 - r + i] for i < r
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 1; j < 8; j++) if ((uint32_t)j == r && 8 - j + i < 8) x = q[8 - j + i];
+            v[i] = x;
+        }
+        st_global_v8(sym + (o & ~7u), v);
     }
     // A stream that ends early leaves the remaining blocks empty (zero coefficients).
     if (valid && seg + 1 == sd.nseg)

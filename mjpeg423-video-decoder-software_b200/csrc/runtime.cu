@@ -341,7 +341,7 @@ int decode_mode(const mjpeg423_b200_ctx* c, const Plan& plan) {
 // in the staged modes, coefficient planes.
 size_t chunk_index_bytes(const Plan& plan, uint32_t f0, uint32_t f1) {
     const size_t blocks = (size_t)(f1 - f0) * 3 * plan.nb, segs = plan.f_seg0[f1] - plan.f_seg0[f0];
-    return blocks * 8 + segs * (size_t)SYM_STRIDE * 4 + 256;
+    return blocks * 8 + 32 + segs * (size_t)SYM_STRIDE * 4 + 256;
 }
 int reserve_chunk_buffers(mjpeg423_b200_ctx* c, const Plan& plan, const std::vector<Chunk>& chunks, int nbuf) {
     size_t idx_bytes = 0, frames = 0;
@@ -376,7 +376,7 @@ EntropyJob make_job(const Plan& plan, const Tables& t, const uint8_t* d_payload_
     const size_t blocks = (size_t)(f1 - f0) * 3 * plan.nb, first_block = (size_t)f0 * 3 * plan.nb;
     uint32_t* w = static_cast<uint32_t*>(d_blkidx);
     j.d_blk_info = reinterpret_cast<uint2*>(w) - first_block;
-    j.d_sym = w + ((2 * blocks + 3) & ~(size_t)3);   // 16-byte aligned; entries are relative to the chunk's first segment
+    j.d_sym = w + ((2 * blocks + 7) & ~(size_t)7);   // 32-byte aligned; entries are relative to the chunk's first segment
     j.sym_seg0 = plan.f_seg0[f0];
     return j;
 }
