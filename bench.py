@@ -35,7 +35,7 @@ WORKLOADS = {
     "480p": (640, 480, 4800, 64, 16, "default", False),         # BASELINE configs[0]/[1] content, longer
     "1080p": (1920, 1080, 2000, 64, 16, "default", False),      # BASELINE configs[2]: the headline config
     "4k": (3840, 2160, 256, 16, 256, "default", False),         # BASELINE configs[3]: dense, entropy-bound
-    "4k-q1": (3840, 2160, 128, 8, 256, "ones", False),          # configs[3] extreme: all-ones quant tables
+    "4k-q1": (3840, 2160, 64, 8, 256, "ones", False),           # configs[3] extreme: all-ones quant tables
     "1080p-8192": (1920, 1080, 8192, 64, 16, "default", True),  # BASELINE configs[4]: fixed total, sharded
 }
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
@@ -95,6 +95,22 @@ class ClockSampler:
         load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(smax) if smax else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous frame range of `rank` when `total` frames are split over `world` ranks."""
+    return total * rank // world, total * (rank + 1) // world
+
+
+def reduce_over_ranks(dist, maxima, sums, device):
+    """MAX-reduce the timings and SUM-reduce the counts over all ranks (no-op for a single process)."""
+    import torch
+    t = torch.tensor(list(maxima), dtype=torch.float64, device=device)
+    c = torch.tensor(list(sums), dtype=torch.float64, device=device)
+    if dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    return [float(x) for x in t.tolist()], [float(x) for x in c.tolist()]
 
 
 def make_stream(wl: str, frames: int, nthreads: int):
@@ -181,7 +197,7 @@ def main():
     if args.frames:
         frames = args.frames
     if strong:
-        lo, hi = frames * rank // world, frames * (rank + 1) // world
+        lo, hi = shard_range(frames, rank, world)
         my_frames = hi - lo
     else:
         my_frames = frames
@@ -264,13 +280,8 @@ def main():
         assert api.frame_hash_host(tail)[0] == want[e2e_frames - 1], "end-to-end output differs from the oracle"
 
     # ---- reduce over ranks ----------------------------------------------------------------------------------------
-    t = torch.tensor([ev_ms, wall_ms, e2e_s], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(my_frames), float(launches), float(e2e_frames)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ev_ms_max, wall_ms_max, e2e_s_max = (float(x) for x in t.tolist())
-    total_frames, total_launches, total_e2e_frames = (float(x) for x in cnt.tolist())
+    (ev_ms_max, wall_ms_max, e2e_s_max), (total_frames, total_launches, total_e2e_frames) = reduce_over_ranks(
+        dist, [ev_ms, wall_ms, e2e_s], [my_frames, launches, e2e_frames], "cuda")
 
     if rank == 0:
         peak, peak_src = measured_peak()
