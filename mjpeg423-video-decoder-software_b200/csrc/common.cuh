@@ -307,6 +307,31 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
                  : "memory");
 }
 
+// Colour conversion of pixels that share one (Cb, Cr) pair -- a block whose chroma blocks are flat.  The
+// chroma terms of ycbcr_to_rgb.c:33-37 are then per-block constants (kr, kg, kb, the "- 128" folded in as in
+// ycc_to_bgra()), and each pixel costs one multiply-add per channel.
+struct FlatChroma {
+    int kr, kg, kb;
+    __device__ __forceinline__ FlatChroma(uint32_t cb, uint32_t cr) {
+        kr = 22970 * (int)cr - 128 * 22970;
+        kg = -5638 * (int)cb - 11700 * (int)cr + 128 * (5638 + 11700);
+        kb = 29032 * (int)cb - 128 * 29032;
+    }
+    __device__ __forceinline__ uint32_t px(uint32_t y) const {
+        const int yy = (int)y * 16384;
+        const uint32_t R = (uint32_t)__vimin_s32_relu((yy + kr) >> 14, 255);
+        const uint32_t G = (uint32_t)__vimin_s32_relu((yy + kg) >> 14, 255);
+        const uint32_t B = (uint32_t)__vimin_s32_relu((yy + kb) >> 14, 255);
+        return B | (G << 8) | (R << 16);
+    }
+    __device__ __forceinline__ void row_store(uint32_t y0, uint32_t y1, uint8_t* dst) const {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[k] = px((y0 >> (8 * k)) & 255u); v[4 + k] = px((y1 >> (8 * k)) & 255u); }
+        st_global_v8(dst, v);
+    }
+};
+
 // One block row (8 pixels) of Y/Cb/Cr packed samples -> 8 BGRA words, stored as one 32-byte sector.
 __device__ __forceinline__ void colour_row_store(uint32_t y0, uint32_t y1, uint32_t cb0, uint32_t cb1, uint32_t cr0,
                                                  uint32_t cr1, uint8_t* dst) {

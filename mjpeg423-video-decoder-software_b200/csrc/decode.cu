@@ -103,23 +103,26 @@ k_decode_coef(const StreamDesc* __restrict__ streams, const uint32_t* __restrict
     }
 }
 
-// ---- fully fused: bitstream + block index -> BGRA ---------------------------------------------------------
+// ---- fully fused: symbol lists + block index -> BGRA ------------------------------------------------------
 // PERSISTENT kernel: one CTA of FUSED_TPB threads per SM (all the shared memory of the SM), every WARP
 // loops over warp tiles of 32 consecutive block positions of one frame.  Warps never synchronise with
 // each other after the table set-up, so a warp that finishes a cheap tile (flat picture area) starts the
-// next one at once and the SM stays at its full 14 resident warps.
+// next one at once and the SM stays at its full 18 resident warps.
 //
 // The body is written as LOOPS over planes, column pairs and rows with its working set in shared
-// memory, not as one unrolled register-resident IDCT: warps drift apart in the data-dependent parse,
+// memory, not as one unrolled register-resident IDCT: warps drift apart in the data-dependent scatter,
 // so the instruction working set has to fit the instruction cache (the unrolled form is ~100 KB of
-// SASS and ran instruction-fetch bound, profiles/r01b).  Shared memory (word-interleaved by thread so
-// that every access below is bank-conflict free; T = FUSED_TPB):
-//   coef  uint4 [8][T]    chunk c = column c of the block: rows 0..7 as int16 (the parser scatters
-//                         straight into this TRANSPOSED layout, so pass 1 reads a column with one LDS.128)
-//   ws    uint2 [32][T]   unit r*4 + c/2 = pass-1 outputs ws[r][c], ws[r][c+1] (int32)
-//   stash u32   [32][T]   word p*16 + 2r + h = samples of plane p (Y, Cb), row r, half h
-constexpr int FUSED_TPB = 448;                                   // 14 warps x 512 B/thread = 224 KB of the SM's 227 KB
-constexpr int FUSED_SMEM = FUSED_TPB * (128 + 256 + 128) + 2 * 64 * 4;
+// SASS and ran instruction-fetch bound, profiles/r01b).  Shared memory, in 16-byte granules interleaved
+// by thread (granule g of thread t at (g*T + t)*16, T = FUSED_TPB; conflict-free for 128-bit access):
+//   ws    granules 0..15   granule cp*4 + r/2 = pass-1 outputs {ws[r][2cp], ws[r][2cp+1], ws[r+1][2cp], ws[r+1][2cp+1]}
+//   coef  granules 8..15   granule 8+c = column c of the block, rows 0..7 as int16.  ALIASES the upper half of
+//                          ws: pass 1 consumes columns 2cp, 2cp+1 in iteration cp and only then writes granules
+//                          4cp..4cp+3, so every coefficient granule is dead before it is overwritten.
+//                          (The parser's zig-zag table scatters straight into this TRANSPOSED layout, so
+//                          pass 1 reads a column with one LDS.128.)
+//   stash words [32][T]    word p*16 + 2r + h = samples of plane p (Y, Cb), row r, half h
+constexpr int FUSED_TPB = 576;                                   // 18 warps x 384 B/thread = 216 KB of the SM's 227 KB
+constexpr int FUSED_SMEM = FUSED_TPB * (256 + 128) + 2 * 64 * 4;
 
 __global__ void __launch_bounds__(FUSED_TPB, 1)
 k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__ blk_info,
@@ -127,10 +130,10 @@ k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__
                const int16_t* __restrict__ quant, uint8_t* __restrict__ out, uint32_t nb, uint32_t wb, uint32_t W,
                uint32_t n_frames) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* s_coef = smem;
-    uint2* s_ws = reinterpret_cast<uint2*>(smem + FUSED_TPB * 128);
-    uint32_t* s_stash = reinterpret_cast<uint32_t*>(smem + FUSED_TPB * 384);
-    uint32_t* s_zq = reinterpret_cast<uint32_t*>(smem + FUSED_TPB * 512);    // 2 x 64 words
+    uint4* s_ws = reinterpret_cast<uint4*>(smem);                                   // granules 0..15
+    uint8_t* s_coef = smem + 8 * FUSED_TPB * 16;                                    // granules 8..15
+    uint32_t* s_stash = reinterpret_cast<uint32_t*>(smem + FUSED_TPB * 256);
+    uint32_t* s_zq = reinterpret_cast<uint32_t*>(smem + FUSED_TPB * 384);           // 2 x 64 words
     const int t = threadIdx.x;
     if (t < 128) {                                                       // zig-zag -> transposed offset | quant
         const int tab = t >> 6, k = t & 63;
@@ -150,16 +153,23 @@ k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__
         const StreamDesc* sd0 = streams + (size_t)f * 3;
         uint8_t* dst = out + ((size_t)f * nb * 64 + ((size_t)(b / wb) * 8 * W + (size_t)(b % wb) * 8)) * 4;
 
-        // Fetch the index entries of all three planes up front (independent, coalesced loads).
-        uint32_t off[3], meta[3];
+        // Fetch the index entries of all three planes and the first PRE list entries of each up front:
+        // 3 + 3*PRE independent loads in flight per lane instead of a dependent load per coefficient.
+        constexpr int PRE = 4;
+        uint32_t meta[3], pre[3][PRE];
+        const uint32_t* lst[3];
 #pragma unroll
         for (int p = 0; p < 3; p++) {
-            const uint32_t gb = sd0[p].block_base + b;
-            const uint2 info = live ? __ldg(blk_info + gb) : make_uint2(0u, 0u);
-            off[p] = info.x;
+            const uint2 info = live ? __ldg(blk_info + sd0[p].block_base + b) : make_uint2(0u, 0u);
+            lst[p] = sym + info.x;
             meta[p] = info.y;
         }
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+#pragma unroll
+            for (int i = 0; i < PRE; i++) pre[p][i] = (uint32_t)i < (meta[p] >> 16) ? __ldg(lst[p] + i) : 0u;
 
+        bool cb_flat = false;                                            // warp-uniform: every Cb block of the tile is DC-only
 #pragma unroll 1
         for (int p = 0; p < 3; p++) {
             // ---- scatter this plane's block into the (zeroed) transposed coefficient slot -----------------
@@ -167,27 +177,30 @@ k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__
             for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(my_coef + c * (FUSED_TPB * 16)) = make_uint4(0, 0, 0, 0);
             // (p is a loop variable: select the pre-fetched registers without dynamic indexing)
             const uint32_t pmeta = p == 0 ? meta[0] : p == 1 ? meta[1] : meta[2];
-            const uint32_t* src = sym + (p == 0 ? off[0] : p == 1 ? off[1] : off[2]);
+            const uint32_t* src = p == 0 ? lst[0] : p == 1 ? lst[1] : lst[2];
             const uint32_t* zq = s_zq + (p ? 64 : 0);
             const uint32_t n = pmeta >> 16;
             *reinterpret_cast<int16_t*>(my_coef) = (int16_t)((int)(int16_t)(pmeta & 0xFFFFu) * (int)(zq[0] >> 16));  // lossless_decode.c:94-95
             uint32_t m_ac = 0, m_any = 1u;
+            auto put = [&](uint32_t ent) {                                // dequantise + scatter one entry (:125)
+                const uint32_t z = zq[ent & 63u];
+                const uint32_t o = z & 0xFFFFu;                           // column * (T*16) + row * 2
+                *reinterpret_cast<int16_t*>(my_coef + o) = (int16_t)(((int)ent >> 16) * (int)(z >> 16));
+                const uint32_t col = o / (FUSED_TPB * 16u);
+                m_any |= 1u << col;
+                if (o & 15u) m_ac |= 1u << col;                           // row >= 1
+            };
+#pragma unroll
+            for (int i = 0; i < PRE; i++) {
+                const uint32_t ent = p == 0 ? pre[0][i] : p == 1 ? pre[1][i] : pre[2][i];
+                if ((uint32_t)i < n) put(ent);
+            }
             const uint32_t nmax = __reduce_max_sync(FULL_MASK, n);        // warp-uniform trip count
-            for (uint32_t i = 0; i < nmax; i += 2) {                      // two independent loads in flight
+            for (uint32_t i = PRE; i < nmax; i += 2) {                    // rest of the list, two loads in flight
                 const uint32_t e0 = i < n ? __ldg(src + i) : 0u;
                 const uint32_t e1 = i + 1 < n ? __ldg(src + i + 1) : 0u;
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const uint32_t ent = h ? e1 : e0;
-                    if (i + h < n) {
-                        const uint32_t z = zq[ent & 63u];
-                        const uint32_t o = z & 0xFFFFu;                   // column * (T*16) + row * 2
-                        *reinterpret_cast<int16_t*>(my_coef + o) = (int16_t)(((int)ent >> 16) * (int)(z >> 16));   // :125
-                        const uint32_t col = o / (FUSED_TPB * 16u);
-                        m_any |= 1u << col;
-                        if (o & 15u) m_ac |= 1u << col;                   // row >= 1
-                    }
-                }
+                if (i < n) put(e0);
+                if (i + 1 < n) put(e1);
             }
             __syncwarp();
             const uint32_t acm = warp_or(m_ac), anym = warp_or(m_any);    // warp-uniform from here on
@@ -207,9 +220,22 @@ k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__
             if (((anym & 0xFEu) | (acm & 1u)) == 0) {
                 // DC-only blocks in the whole warp: both passes collapse to (4*dc + 16) >> 5 (see idct_block()).
                 const int dcv = (int)*reinterpret_cast<const int16_t*>(my_coef);
-                const uint32_t v = clamp255(((dcv << 2) + 16) >> 5) * 0x01010101u;
+                const uint32_t s8 = clamp255(((dcv << 2) + 16) >> 5);
+                const uint32_t v = s8 * 0x01010101u;
+                if (p == 1) cb_flat = true;
+                if (p == 2 && cb_flat) {
+                    // Flat Cb and Cr blocks: the chroma terms are per-block constants.
+                    if (live) {
+                        const FlatChroma fc(s_stash[16 * FUSED_TPB + t] & 255u, s8);
 #pragma unroll 1
-                for (int r = 0; r < 8; r++) emit(r, v, v);
+                        for (int r = 0; r < 8; r++)
+                            fc.row_store(s_stash[(2 * r) * FUSED_TPB + t], s_stash[(2 * r + 1) * FUSED_TPB + t],
+                                         dst + (size_t)r * W * 4);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int r = 0; r < 8; r++) emit(r, v, v);
+                }
                 continue;
             }
             // ---- pass 1: columns, two at a time (idct.c:41-109) --------------------------------------------------
@@ -229,15 +255,17 @@ k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__
                     for (int r = 0; r < 8; r++) { o0[r] = v0; o1[r] = v1; }
                 }
 #pragma unroll
-                for (int r = 0; r < 8; r++) s_ws[(r * 4 + cp) * FUSED_TPB + t] = make_uint2((uint32_t)o0[r], (uint32_t)o1[r]);
+                for (int r = 0; r < 8; r += 2)                   // both column loads above precede these stores (aliasing)
+                    s_ws[(cp * 4 + r / 2) * FUSED_TPB + t] = make_uint4((uint32_t)o0[r], (uint32_t)o1[r], (uint32_t)o0[r + 1], (uint32_t)o1[r + 1]);
             }
             // ---- pass 2: rows (idct.c:116-180) ------------------------------------------------------------------
 #pragma unroll 1
             for (int r = 0; r < 8; r++) {
-                const uint2 a = s_ws[(r * 4 + 0) * FUSED_TPB + t], bq = s_ws[(r * 4 + 1) * FUSED_TPB + t];
+                const uint2* row = reinterpret_cast<const uint2*>(s_ws + (r >> 1) * FUSED_TPB + t) + (r & 1);
+                const uint2 a = row[0], bq = row[4 * FUSED_TPB * 2];
                 int o[8];
                 if (high_half) {
-                    const uint2 cq = s_ws[(r * 4 + 2) * FUSED_TPB + t], dq = s_ws[(r * 4 + 3) * FUSED_TPB + t];
+                    const uint2 cq = row[8 * FUSED_TPB * 2], dq = row[12 * FUSED_TPB * 2];
                     idct8<18>((int)a.x, (int)a.y, (int)bq.x, (int)bq.y, (int)cq.x, (int)cq.y, (int)dq.x, (int)dq.y, o);
                 } else {
                     idct8<18>((int)a.x, (int)a.y, (int)bq.x, (int)bq.y, 0, 0, 0, 0, o);
