@@ -13,18 +13,18 @@ namespace mj {
 // A plane bitstream is cut into fixed SEG_BYTES segments; a segment owns the blocks whose FIRST bit
 // lies inside it.  CP_BITS is the spacing of the merge checkpoints inside a segment.
 // ------------------------------------------------------------------------------------------------
-constexpr int SEG_BYTES = 256;
+constexpr int SEG_BYTES = 512;
 constexpr int SEG_BITS = SEG_BYTES * 8;
-constexpr int CP_BITS = 256;
+constexpr int CP_BITS = 512;
 constexpr int NCP = SEG_BITS / CP_BITS;        // checkpoints per segment (the last one is the segment end)
 constexpr int ENT_TPB = 128;                   // threads per CTA in the entropy kernels
 constexpr int MIN_BLOCK_BITS = 12;             // DC size 0 + END
 constexpr uint32_t RUNAWAY_BITS = 8192;        // parse guard for non-conforming / speculative garbage
 constexpr uint32_t MAX_STREAM_BYTES = 1u << 28; // bit positions are 32-bit
 // Symbol list: the index pass writes every coded AC coefficient of a segment's blocks as one 32-bit entry
-// (zig-zag index | amplitude << 16) into a fixed-stride region.  A segment owns at most 2048/9 = 227 coded
-// symbols that start inside it plus the rest of its last block (a block has at most 63 AC coefficients).
-constexpr uint32_t SYM_STRIDE = 320;             // entries per segment (>= 227 + 63)
+// (zig-zag index | amplitude << 16) into a fixed-stride region.  A segment owns at most SEG_BITS/9 coded
+// symbols (>= 9 bits each) that start inside it plus the rest of its last block (<= 63 AC coefficients).
+constexpr uint32_t SYM_STRIDE = (SEG_BYTES * 8 / 9 + 63 + 7) / 8 * 8;   // entries per segment, a multiple of 8
 
 // One plane bitstream of one frame (built by the host from the 16-byte frame headers,
 // LIB/decoder/mjpeg423_decoder.c:94-107).
