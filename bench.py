@@ -288,23 +288,34 @@ def main():
         fps = total_frames * args.steps / (ev_ms_max / 1e3)
         Cbar = payload_bytes / my_frames
         n = my_frames
+        blocks = (3 * P // 64) * n
+        lists = 4 * ps["list_entries"]
         stage = {
-            # ALGORITHMIC bytes per launch: C = compressed bytes, P = pixels per frame,
-            # 3*nb = P*3/64 blocks per frame; the block index is 6 bytes per block
-            "entropy_sync": {"ms": ps["sync_ms"], "bytes": payload_bytes, "kernels": "k_entropy_sync"},
+            # ALGORITHMIC bytes per step: C = compressed bytes, P = pixels per frame; symbol lists are
+            # 4 bytes per coded coefficient, the block index 8 bytes per block, per-segment state 16 bytes
+            "entropy_sync": {"ms": ps["sync_ms"], "bytes": payload_bytes + 12 * ps["segments"], "kernels": "k_entropy_sync"},
             "entropy_chain": {"ms": ps["chain_ms"], "bytes": 16 * ps["segments"], "kernels": "k_entropy_chain"},
-            "entropy_index": {"ms": ps["index_ms"], "bytes": payload_bytes + 6 * (3 * P // 64) * n, "kernels": "k_entropy_index"},
-            "decode_fused": {"ms": ps["decode_ms"], "bytes": payload_bytes + (6 * (3 * P // 64) + 4 * P) * n,
-                             "kernels": "k_decode_fused"},
+            "entropy_index": {"ms": ps["index_ms"], "bytes": payload_bytes + lists + 8 * blocks, "kernels": "k_entropy_index"},
+            "decode_fused": {"ms": ps["decode_ms"], "bytes": lists + 8 * blocks + 4 * P * n, "kernels": "k_decode_fused"},
         }
         for s in stage.values():
             s["GBs"] = s["bytes"] / max(s["ms"], 1e-9) / 1e6
             s["frac_of_hbm_peak"] = s["GBs"] / peak
         dom = max(stage, key=lambda k: stage[k]["ms"])
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (bytes per frame of
+        # the same workload, scaled to this step's frames); null if no capture is on file for it.
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                cap = json.load(f).get(args.workload, {}).get(stage[dom]["kernels"])
+            if cap:
+                traffic = cap["dram_bytes_per_frame"] * n
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": stage[dom]["kernels"], "achieved": stage[dom]["GBs"], "peak": peak,
-                    "unit": "GB/s", "frac": stage[dom]["GBs"] / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": stage[dom]["bytes"],
-                    "launch_ms": stage[dom]["ms"],
+                    "unit": "GB/s", "frac": stage[dom]["GBs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_step": stage[dom]["bytes"], "step_ms_in_kernel": stage[dom]["ms"],
+                    "launches_per_step": ps["kernel_launches"] // 4,
                     "pipeline_headline": {"bytes_per_frame": Cbar + 4 * P, "GBs": fps / world * (Cbar + 4 * P) / 1e9,
                                           "frac": fps / world * (Cbar + 4 * P) / 1e9 / peak}}
         cpu_baseline = None

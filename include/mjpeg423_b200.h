@@ -121,6 +121,7 @@ typedef struct {
     uint64_t payload_bytes;      /* compressed bytes consumed (sum of plane streams) */
     uint64_t segments, fixups;   /* bitstream segments / segments re-parsed by the chain kernel */
     uint64_t frames;
+    uint64_t list_entries;       /* coded AC coefficients written to the symbol lists (4 bytes each) */
 } mjpeg423_b200_stats;
 
 enum {

@@ -63,7 +63,7 @@ class _Stats(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("sync_ms", C.c_float), ("chain_ms", C.c_float), ("index_ms", C.c_float),
                 ("decode_ms", C.c_float), ("idct_colour_ms", C.c_float), ("idct_ms", C.c_float),
                 ("colour_ms", C.c_float), ("kernel_launches", C.c_uint64), ("payload_bytes", C.c_uint64),
-                ("segments", C.c_uint64), ("fixups", C.c_uint64), ("frames", C.c_uint64)]
+                ("segments", C.c_uint64), ("fixups", C.c_uint64), ("frames", C.c_uint64), ("list_entries", C.c_uint64)]
 
 
 @dataclass

@@ -64,7 +64,7 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     int rc;
     if ((rc = s_in.reserve(len + 64))) return rc;
     if ((rc = s_tab.reserve(256 + 256 + b_sync + b_write))) return rc;
-    if ((rc = s_seg.reserve((size_t)sd.nseg * 16 + 64))) return rc;
+    if ((rc = s_seg.reserve((size_t)sd.nseg * 16 + 96))) return rc;
     if ((rc = s_idx.reserve((size_t)num_blocks * 8 + (size_t)sd.nseg * SYM_STRIDE * 4 + 128))) return rc;
     if ((rc = s_mid.reserve(coef_bytes))) return rc;
     uint8_t* tab = s_tab.as<uint8_t>();
@@ -94,7 +94,7 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     j.sym_seg0 = 0;
     uint32_t* d_ids = reinterpret_cast<uint32_t*>(tab + 256 + 128);     // one id: stream 0
     CUX(cudaMemsetAsync(d_ids, 0, 4, s));
-    CUX(cudaMemsetAsync(j.d_fixups, 0, 8, s));
+    CUX(cudaMemsetAsync(j.d_fixups, 0, 16, s));
     CUX(launch_entropy_sync(j, s));
     CUX(launch_entropy_chain(j, s));
     CUX(launch_entropy_index(j, s));

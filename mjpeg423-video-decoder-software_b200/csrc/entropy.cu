@@ -269,7 +269,8 @@ __global__ void __launch_bounds__(ENT_TPB)
 k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
                 const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ seg_entry,
                 const uint32_t* __restrict__ seg_cd, const uint32_t* __restrict__ seg_first,
-                uint2* __restrict__ blk_info, uint32_t* __restrict__ sym, uint32_t sym_seg0) {
+                uint2* __restrict__ blk_info, uint32_t* __restrict__ sym, uint32_t sym_seg0,
+                unsigned long long* __restrict__ n_entries) {
     const int t = threadIdx.x;
     const TileDesc td = tiles[blockIdx.x];
     const StreamDesc sd = streams[td.stream];
@@ -323,6 +324,12 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
         }
         st_global_v8(sym + (o & ~7u), v);
     }
+    {   // statistics: list entries written by this launch (one atomic per warp)
+        uint32_t mine = valid ? min(o, o_end) - o_base : 0u;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(FULL_MASK, mine, d);
+        if ((t & 31) == 0 && mine) atomicAdd(n_entries, (unsigned long long)mine);
+    }
     // A stream that ends early leaves the remaining blocks empty (zero coefficients).
     if (valid && seg + 1 == sd.nseg)
         for (uint32_t b = first + cnt; b < sd.nb; b++) blk_info[sd.block_base + b] = make_uint2(0, 0);
@@ -347,7 +354,8 @@ cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s) {
 cudaError_t launch_entropy_index(const EntropyJob& j, cudaStream_t s) {
     if (j.n_write_tiles == 0) return cudaSuccess;
     k_entropy_index<<<j.n_write_tiles, ENT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_write_tiles, j.d_seg_entry,
-                                                        j.d_seg_cd, j.d_seg_first, j.d_blk_info, j.d_sym, j.sym_seg0);
+                                                        j.d_seg_cd, j.d_seg_first, j.d_blk_info, j.d_sym, j.sym_seg0,
+                                                        j.d_fixups + 1);
     return cudaGetLastError();
 }
 

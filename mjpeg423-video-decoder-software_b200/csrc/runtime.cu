@@ -298,7 +298,7 @@ int upload_tables(mjpeg423_b200_ctx* c, const Plan& plan, Tables& t, cudaStream_
     int rc = c->tables.reserve(b_streams + b_sync + b_write + 256);
     if (rc) return rc;
     const size_t nseg = plan.f_seg0.empty() ? 0 : plan.f_seg0.back();
-    rc = c->segs.reserve(4 * align256(nseg * 4) + align256(plan.streams.size() * 4) + 256);
+    rc = c->segs.reserve(4 * align256(nseg * 4) + align256(plan.streams.size() * 4) + 256);   // ... + 2 x u64 counters
     if (rc) return rc;
     t = tables_of(c, plan);
     CU(cudaMemcpyAsync(t.streams, plan.streams.data(), plan.streams.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, s));
@@ -444,15 +444,16 @@ int accumulate_profile(mjpeg423_b200_ctx* c, cudaEvent_t* prof) {
 
 // After all chunks: fetch the fix-up counter and (optionally) check that every stream held nb blocks.
 int finish_stats(mjpeg423_b200_ctx* c, const Plan& plan, const Tables& t, cudaStream_t s) {
-    unsigned long long fix = 0;
-    CU(cudaMemcpyAsync(&fix, t.fixups, 8, cudaMemcpyDeviceToHost, s));
+    unsigned long long fix[2] = {0, 0};
+    CU(cudaMemcpyAsync(fix, t.fixups, 16, cudaMemcpyDeviceToHost, s));
     std::vector<uint32_t> blocks;
     if (c->validate) {
         blocks.resize(plan.streams.size());
         CU(cudaMemcpyAsync(blocks.data(), t.stream_blocks, blocks.size() * 4, cudaMemcpyDeviceToHost, s));
     }
     CU(cudaStreamSynchronize(s));
-    c->stats.fixups = fix;
+    c->stats.fixups = fix[0];
+    c->stats.list_entries = fix[1];
     c->stats.segments = plan.f_seg0.back();
     c->stats.payload_bytes = plan.stream_bytes;
     c->stats.frames = plan.n;
@@ -508,7 +509,7 @@ extern "C" int mjpeg423_b200_decode_resident(mjpeg423_b200_ctx* c, void* d_out) 
     cudaStream_t st[2] = {c->s_compute, c->s_aux};
     cudaEvent_t ev_start = c->ev[0], ev_stop = c->ev[1], ev_fork = c->ev[2], ev_join = c->ev[3];
     cudaEvent_t* prof = c->profile ? &c->ev[4] : nullptr;
-    CU(cudaMemsetAsync(t.fixups, 0, 8, st[0]));
+    CU(cudaMemsetAsync(t.fixups, 0, 16, st[0]));
     CU(cudaEventRecord(ev_start, st[0]));
     if (nbuf == 2) { CU(cudaEventRecord(ev_fork, st[0])); CU(cudaStreamWaitEvent(st[1], ev_fork, 0)); }
     for (size_t k = 0; k < c->chunks.size(); k++) {
@@ -550,7 +551,7 @@ extern "C" int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* c, int16_t* d_c
     const Chunk& ch = c->chunks[0];
     EntropyJob j = make_job(plan, t, c->payload.as<uint8_t>(), 0, plan.n, c->blkidx[0].p);
     cudaEvent_t* e = &c->ev[4];
-    CU(cudaMemsetAsync(t.fixups, 0, 8, s));
+    CU(cudaMemsetAsync(t.fixups, 0, 16, s));
     CU(cudaEventRecord(e[0], s));
     CU(launch_entropy_sync(j, s));
     CU(cudaEventRecord(e[1], s));
@@ -644,7 +645,7 @@ extern "C" int mjpeg423_b200_decode_frames(mjpeg423_b200_ctx* c, const uint8_t* 
     cudaEvent_t* ev_comp = &c->ev[4];   // [2]: chunk decoded (payload slot consumed, out slot produced)
     cudaEvent_t* ev_out = &c->ev[6];    // [2]: out slot read back
     cudaEvent_t* prof = c->profile ? &c->ev[8] : nullptr;
-    CU(cudaMemsetAsync(t.fixups, 0, 8, c->s_in));
+    CU(cudaMemsetAsync(t.fixups, 0, 16, c->s_in));
     CU(cudaEventRecord(ev_start, c->s_in));
     CU(cudaStreamWaitEvent(c->s_compute, ev_start, 0));
     for (size_t k = 0; k < c->chunks.size(); k++) {

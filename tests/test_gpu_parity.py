@@ -238,6 +238,23 @@ def test_stream_bit_exact(checker, dec, W, H, n, amp, flat):
     assert st["frames"] == n and st["kernel_launches"] >= 4
 
 
+def test_stream_4k_dense_all_ones_quant(checker, dec):
+    """BASELINE configs[3] extreme: 3840x2160, full-range noise, all-ones quantisation tables passed through the
+    `quant` parameter on both sides (dense coefficients, amplitudes up to 11 bits, ~25 bit/px)."""
+    ones = np.ones(64, np.int16)
+    mpg = synth.synth_mpg(3840, 2160, 2, 0, 256, 0, ones, ones)
+    assert mpg.size / 2 > 20e6                               # really is the dense regime
+    want = checker.decode_mpg(mpg, yq=ones, cq=ones, nthreads=2)
+    dec.set_quant(ones, ones)
+    try:
+        got = dec.decode_frames(mpg)
+        assert np.array_equal(got, want)
+        st = dec.stats()
+        assert st["list_entries"] > 0.9 * 2 * 3 * (3840 * 2160 // 64) * 63   # nearly every coefficient is coded
+    finally:
+        dec.set_quant(None, None)
+
+
 def test_stream_640x480_300_frames_bit_exact(checker, dec):
     """BASELINE configs[1]: the 640x480 x 300 stream, every frame compared byte for byte."""
     mpg = synth.synth_mpg(640, 480, 300, 0, 16, 0)
