@@ -307,27 +307,40 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
                  : "memory");
 }
 
-// Colour conversion of pixels that share one (Cb, Cr) pair -- a block whose chroma blocks are flat.  The
-// chroma terms of ycbcr_to_rgb.c:33-37 are then per-block constants (kr, kg, kb, the "- 128" folded in as in
-// ycc_to_bgra()), and each pixel costs one multiply-add per channel.
+// Colour conversion of pixels that share one (Cb, Cr) pair -- a block whose chroma blocks are flat.
+// Because Y << 14 has no low bits, NORMALIZE_RGB((Y << 14) + k) == clamp(Y + (k >> 14), 0, 255) exactly
+// (arithmetic shift = floor; k = the chroma terms of ycbcr_to_rgb.c:33-37, per-block constants here, |k >> 14| < 256).
+// Two pixels are processed per register in signed 16-bit lanes, biased by 256 so that the packed add never
+// borrows across lanes: lane = Y + K + 256, clamped to [256, 511] with two VIMNMX.S16x2; the low byte of each
+// lane is the result and the high byte (always 1, msb clear) provides the zero alpha through PRMT's sign mode.
 struct FlatChroma {
-    int kr, kg, kb;
+    uint32_t kr2, kg2, kb2;
     __device__ __forceinline__ FlatChroma(uint32_t cb, uint32_t cr) {
-        kr = 22970 * (int)cr - 128 * 22970;
-        kg = -5638 * (int)cb - 11700 * (int)cr + 128 * (5638 + 11700);
-        kb = 29032 * (int)cb - 128 * 29032;
+        const int cbb = (int)cb - 128, crr = (int)cr - 128;
+        kr2 = (uint32_t)(((22970 * crr) >> 14) + 256) * 0x00010001u;
+        kg2 = (uint32_t)(((-5638 * cbb - 11700 * crr) >> 14) + 256) * 0x00010001u;
+        kb2 = (uint32_t)(((29032 * cbb) >> 14) + 256) * 0x00010001u;
     }
-    __device__ __forceinline__ uint32_t px(uint32_t y) const {
-        const int yy = (int)y * 16384;
-        const uint32_t R = (uint32_t)__vimin_s32_relu((yy + kr) >> 14, 255);
-        const uint32_t G = (uint32_t)__vimin_s32_relu((yy + kg) >> 14, 255);
-        const uint32_t B = (uint32_t)__vimin_s32_relu((yy + kb) >> 14, 255);
-        return B | (G << 8) | (R << 16);
+    // PRMT with the selector's sign-replicate bit (bit 3 of a nibble); __byte_perm() masks that bit off.
+    static __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+        uint32_t d;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+        return d;
+    }
+    static __device__ __forceinline__ uint32_t clamp2(uint32_t x) { return __vmaxs2(__vmins2(x, 0x01FF01FFu), 0x01000100u); }
+    // y2 = two Y samples in 16-bit lanes -> two BGRA words
+    __device__ __forceinline__ void px2(uint32_t y2, uint32_t& p0, uint32_t& p1) const {
+        const uint32_t r = clamp2(y2 + kr2), g = clamp2(y2 + kg2), b = clamp2(y2 + kb2);
+        const uint32_t bg = __byte_perm(b, g, 0x6240);       // B0 G0 B1 G1
+        p0 = prmt(bg, r, 0xD410);                            // B0 G0 R0 0
+        p1 = prmt(bg, r, 0xF632);                            // B1 G1 R1 0
     }
     __device__ __forceinline__ void row_store(uint32_t y0, uint32_t y1, uint8_t* dst) const {
         uint32_t v[8];
-#pragma unroll
-        for (int k = 0; k < 4; k++) { v[k] = px((y0 >> (8 * k)) & 255u); v[4 + k] = px((y1 >> (8 * k)) & 255u); }
+        px2(__byte_perm(y0, 0, 0x4140), v[0], v[1]);
+        px2(__byte_perm(y0, 0, 0x4342), v[2], v[3]);
+        px2(__byte_perm(y1, 0, 0x4140), v[4], v[5]);
+        px2(__byte_perm(y1, 0, 0x4342), v[6], v[7]);
         st_global_v8(dst, v);
     }
 };
