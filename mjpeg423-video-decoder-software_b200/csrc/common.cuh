@@ -48,58 +48,6 @@ struct TileDesc {
 };
 
 // ------------------------------------------------------------------------------------------------
-// MSB-first bit reader over global memory.  Replaces update_buffer / INPUT_BITS
-// (LIB/decoder/lossless_decode.c:139-162,207); only the number of consumed bits is observable, so the
-// window mechanics are free: two consecutive big-endian 32-bit words (w0 = current, w1 = next) and a bit
-// offset into w0.  The next 32 stream bits are ONE funnel shift; consuming bits is an add, and when the
-// offset crosses a word the look-ahead word moves down and the following word is fetched -- a whole word
-// (3-4 symbols) before it is needed, which hides most of the load latency.  The payload buffer is padded
-// so that reads up to 16 bytes past any stream end are in bounds.
-// ------------------------------------------------------------------------------------------------
-struct BitReader {
-    const uint32_t* wp;    // next aligned word to fetch
-    uint32_t w0, w1;       // current and look-ahead word, MSB first
-    uint32_t off;          // consumed bits of w0, 0..31
-
-    __device__ static __forceinline__ const uint32_t* word_ptr(const uint8_t* base, uint32_t bitpos) {
-        return reinterpret_cast<const uint32_t*>((reinterpret_cast<uintptr_t>(base) + (bitpos >> 3)) & ~(uintptr_t)3);
-    }
-    __device__ __forceinline__ void init(const uint8_t* base, uint32_t bitpos) {
-        const uint32_t* p = word_ptr(base, bitpos);
-        init_loaded(base, bitpos, __ldg(p), __ldg(p + 1));
-    }
-    // Two-step form: fetch word_ptr()[0..1] early (e.g. for several streams at once), start later.
-    __device__ __forceinline__ void init_loaded(const uint8_t* base, uint32_t bitpos, uint32_t raw0, uint32_t raw1) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(base) + (bitpos >> 3);
-        off = (uint32_t)(a & 3u) * 8u + (bitpos & 7u);
-        wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3) + 2;
-        w0 = __byte_perm(raw0, 0, 0x0123);
-        w1 = __byte_perm(raw1, 0, 0x0123);
-    }
-    __device__ __forceinline__ uint32_t top() const { return __funnelshift_l(w1, w0, off); }   // next 32 bits
-    __device__ __forceinline__ void skip(uint32_t n) {                                         // n <= 31
-        off += n;
-        if (off >= 32u) {
-            off -= 32u;
-            w0 = w1;
-            w1 = __byte_perm(__ldg(wp), 0, 0x0123);
-            wp++;
-        }
-    }
-};
-
-// JPEG VLI sign extension: HUFF_EXTEND, LIB/decoder/lossless_decode.c:204.  size in 0..15; size 0 gives 0.
-// (amp < 2^(size-1) ? amp - 2^size + 1 : amp, written without the undefined shifts of the macro.)
-__device__ __forceinline__ int vli_extend(uint32_t amp, uint32_t size) {
-    const uint32_t full = 1u << size;
-    return (int)amp - ((amp < (full >> 1)) ? (int)(full - 1u) : 0);
-}
-// The `size` amplitude bits that follow a `hdr`-bit header in the 32-bit window t (0 for size 0).
-__device__ __forceinline__ uint32_t amp_bits(uint32_t t, uint32_t hdr, uint32_t size) {
-    return ((t << hdr) >> 1) >> (31u - size);
-}
-
-// ------------------------------------------------------------------------------------------------
 // Symbol stepper shared by every segment-parallel pass (speculative parse, merge, chain re-parse,
 // block index) so that they all follow ONE trajectory function.  The passes run a single flat loop,
 // one symbol per iteration for every lane; step() is branch-free (DC/AC and block-end handling are
@@ -107,68 +55,82 @@ __device__ __forceinline__ uint32_t amp_bits(uint32_t t, uint32_t hdr, uint32_t 
 //   DC symbol  input_DC  LIB/decoder/lossless_decode.c:210-224  (4-bit size + amplitude)
 //   AC symbol  input_AC  :227-246 (4-bit run, 4-bit size, amplitude); size 0: run 15 = ZRL else END
 //   block loop :101-133; `index` is uint8_t there and wraps, so it does here.
-// A block is also ended when it has consumed `budget` bits: memory safety on non-conforming input and
-// on speculative garbage (conforming blocks are <= 1212 bits).
+// A block is also ended when it reaches `flim` = min(block start + RUNAWAY_BITS, end of stream): memory
+// safety and termination on non-conforming input and on speculative garbage (conforming blocks are
+// <= 1212 bits).
+//
+// Bit window (replaces update_buffer / INPUT_BITS, lossless_decode.c:139-162,207; only the number of
+// consumed bits is observable, so the mechanics are free): two consecutive big-endian 32-bit words
+// (w0 = current, w1 = next).  Positions are counted from the ALIGNED word that holds the stream's first
+// byte ("f" positions = stream bit position + bias, bias = 8 * (address & 3)), so the offset into w0 is
+// simply fpos & 31: the next 32 stream bits are ONE funnel shift (which takes its amount mod 32) and a
+// word crossing is bit 5 of fpos flipping.  The look-ahead word is fetched a whole word (3-4 symbols)
+// before it is needed.  The payload buffer is padded: reads up to 16 bytes past any stream end are in
+// bounds.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t block_budget(uint32_t blk_start, uint32_t total_bits) {
-    return min(RUNAWAY_BITS, total_bits - blk_start);
+__device__ __forceinline__ uint32_t stream_bias(const uint8_t* base) {
+    return (uint32_t)(reinterpret_cast<uintptr_t>(base) & 3u) * 8u;
 }
 
 struct Parser {
-    BitReader r;
-    uint32_t pos;          // bit position of the next symbol
-    uint32_t blk_start;    // bit position of the current block's DC symbol
-    uint32_t budget;       // block_budget(blk_start)
+    const uint32_t* wp;    // next aligned word to fetch
+    uint32_t w0, w1;       // current and look-ahead word, MSB first
+    uint32_t fpos;         // f position of the next symbol
+    uint32_t flim;         // the current block is ended at or after this f position
     uint32_t idx;          // zig-zag index of the next AC coefficient
-    bool is_dc;            // next symbol is a DC symbol (= we are at a block start)
+    uint32_t nh;           // minus the header length of the next symbol: -4 = DC (a block start), -8 = AC
 
-    __device__ __forceinline__ void start(const uint8_t* base, uint32_t bitpos, uint32_t total_bits) {
-        r.init(base, bitpos);
-        pos = blk_start = bitpos;
-        budget = block_budget(bitpos, total_bits);
+    // fbits = f position to start at (a block start), ftotal = f position of the end of the stream.
+    __device__ __forceinline__ void start(const uint8_t* base, uint32_t fbits, uint32_t ftotal) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)3) + (fbits >> 5);
+        w0 = __byte_perm(__ldg(w), 0, 0x0123);
+        w1 = __byte_perm(__ldg(w + 1), 0, 0x0123);
+        wp = w + 2;
+        fpos = fbits;
+        flim = min(fbits + RUNAWAY_BITS, ftotal);
         idx = 1;
-        is_dc = true;
+        nh = (uint32_t)-4;
     }
+    __device__ __forceinline__ bool at_block_start() const { return nh == (uint32_t)-4; }
+
     // What the last step() consumed.
     struct Sym {
         bool dc;           // it was the block's DC symbol
         bool coded;        // it was a non-zero AC coefficient ...
         uint32_t at;       // ... at this zig-zag index (may be >= 64 on non-conforming input: ignore then)
-        int e;             // amplitude of the DC / AC coefficient (0 for END and ZRL)
+        int e;             // amplitude of the DC / coded AC coefficient (HUFF_EXTEND, :204); 0 for a size-0 DC symbol,
+                           // unspecified for END / ZRL
     };
     // Consume one symbol.  Returns true when it ended the block (the parser is then positioned on the
-    // next block's DC symbol).
-    __device__ __forceinline__ bool step(uint32_t total_bits, Sym& sym) {
-        const uint32_t t = r.top();
-        const bool dc = is_dc;
-        const uint32_t hdr = dc ? 4u : 8u;
-        const uint32_t rs = t >> (32u - hdr);
-        const uint32_t size = rs & 15u, run = rs >> 4;          // run == 0 for a DC symbol (rs < 16)
-        const uint32_t len = hdr + size;
-        r.skip(len);
-        pos += len;
-        const bool coded = size != 0u && !dc;                   // a non-zero AC coefficient
-        const uint32_t adv = (dc ? 1u : idx) + (dc ? 0u : (size == 0u ? 16u : run));
-        const uint32_t at = adv & 255u;                         // DC: 1; ZRL: idx+16; coefficient: its zig-zag index
-        idx = at + (coded ? 1u : 0u);
-        bool end = (!dc && size == 0u && run != 15u) || (coded && at >= 63u);   // END symbol / coefficient 63
-        end = end || (pos - blk_start) >= budget;
-        is_dc = end;
-        if (end) {
-            blk_start = pos;
-            budget = block_budget(pos, total_bits);
+    // next block's DC symbol).  WANT_E = false skips the amplitude of AC symbols (sym.e valid for DC only).
+    __device__ __forceinline__ bool step(uint32_t ftotal, Sym& sym) {
+        const uint32_t t = __funnelshift_l(w1, w0, fpos);               // next 32 stream bits
+        const bool dc = nh == (uint32_t)-4;
+        const uint32_t rs = __funnelshift_r(t, 0u, nh);                 // t >> (32 - header bits): the 4 / 8 header bits
+        const uint32_t size = rs & 15u, run = rs >> 4;                  // run == 0 for a DC symbol (rs < 16)
+        const uint32_t fnew = fpos + size - nh;
+        // amplitude: the `size` bits after the header, JPEG VLI sign extension (HUFF_EXTEND): a field whose top
+        // bit is clear stands for field - 2^size + 1.  size 0 gives 0.
+        const uint32_t v = t << (0u - nh);
+        const uint32_t amp = (v >> 1) >> (31u ^ size);
+        const int e = (int)amp + (((int)v >= 0) ? (int)(0xFFFFFFFFu << size) + 1 : 0);
+        if ((fpos ^ fnew) & 32u) {                                      // crossed into w1: fetch the word after it
+            w0 = w1;
+            w1 = __byte_perm(__ldg(wp), 0, 0x0123);
+            wp++;
         }
+        const bool szd = size != 0u || dc;
+        const bool coded = size != 0u && !dc;                           // a non-zero AC coefficient
+        const uint32_t at = (idx + (szd ? run : 16u)) & 255u;           // DC: idx (1); ZRL: idx + 16; coefficient: its index
+        const bool end = (!szd && run != 15u) || (coded && at >= 63u) || fnew >= flim;   // END / coefficient 63 / guard
+        idx = end ? 1u : at + (coded ? 1u : 0u);
+        nh = end ? (uint32_t)-4 : (uint32_t)-8;
+        if (end) flim = min(fnew + RUNAWAY_BITS, ftotal);
+        fpos = fnew;
         sym.dc = dc;
         sym.coded = coded;
         sym.at = at;
-        sym.e = vli_extend(amp_bits(t, hdr, size), size);
-        return end;
-    }
-    // Parse-only form: dc_e receives the DC amplitude when the symbol was a DC symbol, else 0.
-    __device__ __forceinline__ bool step(uint32_t total_bits, int& dc_e) {
-        Sym sym;
-        const bool end = step(total_bits, sym);
-        dc_e = sym.dc ? sym.e : 0;
+        sym.e = e;
         return end;
     }
 };

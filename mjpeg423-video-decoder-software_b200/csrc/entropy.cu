@@ -28,26 +28,37 @@
 
 namespace mj {
 
+// All positions inside the kernels are "f" positions (stream bit position + stream_bias(), see Parser);
+// the per-segment arrays in global memory hold plain stream bit positions.
+//
+// fstop_eos: a block start at or after this f position cannot hold a block any more (fewer than
+// MIN_BLOCK_BITS left): the stream's trailing pad bits.
+__device__ __forceinline__ uint32_t eos_stop(uint32_t ftotal) {
+    return ftotal >= (uint32_t)MIN_BLOCK_BITS ? ftotal - (MIN_BLOCK_BITS - 1) : 0u;
+}
+
 // Parse from block start `entry` to the first block start at or after seg_end (or the end of the
 // stream).  Returns the exit position; cnt / dc receive the blocks started and their DC sum mod 2^16.
+// (f positions.)
 __device__ __forceinline__ uint32_t parse_segment(const uint8_t* base, uint32_t entry, uint32_t seg_end,
-                                                  uint32_t total_bits, uint32_t& cnt, uint32_t& dc) {
+                                                  uint32_t ftotal, uint32_t& cnt, uint32_t& dc) {
     cnt = 0;
     int dcsum = 0;
     uint32_t pos = entry;
-    if (pos < seg_end && pos + MIN_BLOCK_BITS <= total_bits) {
+    const uint32_t stop = min(seg_end, eos_stop(ftotal));
+    if (pos < stop) {
         Parser ps;
-        ps.start(base, entry, total_bits);
+        ps.start(base, entry, ftotal);
         for (;;) {
-            int e;
-            const bool end = ps.step(total_bits, e);
-            dcsum += e;
+            Parser::Sym y;
+            const bool end = ps.step(ftotal, y);
+            dcsum += y.dc ? y.e : 0;
             if (end) {
                 cnt++;
-                if (ps.pos >= seg_end || ps.pos + MIN_BLOCK_BITS > total_bits) break;
+                if (ps.fpos >= stop) break;
             }
         }
-        pos = ps.pos;
+        pos = ps.fpos;
     }
     dc = (uint32_t)dcsum & 0xFFFFu;
     return pos;
@@ -61,19 +72,22 @@ struct Resolved { uint32_t exit_pos, cnt, dc; };
 
 // Resolve segment [seg_start, seg_end) for true entry E against the recorded speculative trajectory.
 // WARP-COLLECTIVE (lanes with nothing to resolve pass need = false): the symbol loop runs under a warp
-// vote so the lanes re-converge every iteration.
+// vote so the lanes re-converge every iteration.  The true trajectory is compared with the recorded one
+// at its first block start at or after every checkpoint boundary (once merged, that IS the checkpoint).
 __device__ __forceinline__ Resolved resolve_by_merge(const uint8_t* base, uint32_t E, uint32_t seg_start,
-                                                     uint32_t seg_end, uint32_t total_bits,
+                                                     uint32_t seg_end, uint32_t ftotal,
                                                      const uint32_t (*s_pos)[ENT_TPB], const uint32_t (*s_cd)[ENT_TPB],
                                                      int t, bool need) {
     const uint32_t spec_exit = s_pos[NCP - 1][t], spec_cd = s_cd[NCP - 1][t];
+    const uint32_t fstop_eos = eos_stop(ftotal);
     Resolved rs{E, 0, 0};
     bool active = need;
-    if (active && (E >= seg_end || E + MIN_BLOCK_BITS > total_bits)) active = false;   // owns nothing
+    if (active && (E >= seg_end || E >= fstop_eos)) active = false;   // owns nothing
     if (active && E == seg_start) {                      // speculation started on the true entry
         rs.exit_pos = spec_exit; rs.cnt = spec_cd & 0xFFFFu; rs.dc = spec_cd >> 16;
         active = false;
     }
+    uint32_t next_cp = seg_start + CP_BITS;
     if (active && E >= seg_start + CP_BITS) {            // E itself may be a recorded block start
         const int j = (int)((E - seg_start) / CP_BITS) - 1;
         if (s_pos[j][t] == E) {
@@ -83,33 +97,37 @@ __device__ __forceinline__ Resolved resolve_by_merge(const uint8_t* base, uint32
             rs.dc = ((spec_cd >> 16) - (at >> 16)) & 0xFFFFu;
             active = false;
         }
+        next_cp = seg_start + (uint32_t)(j + 2) * CP_BITS;   // first boundary after E
     }
     Parser ps;
-    if (active) ps.start(base, E, total_bits);
+    if (active) ps.start(base, E, ftotal);
     int dcsum = 0;
     uint32_t cnt = 0;
     const bool parsed = active;
+    uint32_t next_stop = min(next_cp, fstop_eos);
     while (__any_sync(FULL_MASK, active)) {
         if (active) {
-            int e;
-            const bool end = ps.step(total_bits, e);
-            dcsum += e;
-            if (end) {
-                cnt++;
-                const uint32_t pos = ps.pos;
-                bool merged = false;
-                if (pos >= seg_start + CP_BITS) {
+            Parser::Sym y;
+            const bool end = ps.step(ftotal, y);
+            dcsum += y.dc ? y.e : 0;
+            cnt += end ? 1u : 0u;
+            if (end && ps.fpos >= next_stop) {           // rare: first block start past a boundary / end of stream
+                const uint32_t pos = ps.fpos;
+                bool done = false;
+                if (pos >= next_cp) {
                     const int j = (int)min((uint32_t)NCP, (pos - seg_start) / CP_BITS) - 1;
                     if (s_pos[j][t] == pos) {            // merged with the speculative trajectory
                         const uint32_t at = s_cd[j][t];
                         cnt += (spec_cd & 0xFFFFu) - (at & 0xFFFFu);
                         dcsum += (int)(spec_cd >> 16) - (int)(at >> 16);
                         rs.exit_pos = spec_exit;
-                        merged = true;
+                        done = true;
                     }
+                    next_cp = seg_start + (uint32_t)(j + 2) * CP_BITS;
                 }
-                if (merged) active = false;
-                else if (pos >= seg_end || pos + MIN_BLOCK_BITS > total_bits) { rs.exit_pos = pos; active = false; }
+                if (!done && (pos >= seg_end || pos >= fstop_eos)) { rs.exit_pos = pos; done = true; }
+                if (done) active = false;
+                next_stop = min(next_cp, fstop_eos);
             }
         }
     }
@@ -121,7 +139,7 @@ __global__ void __launch_bounds__(ENT_TPB)
 k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
                const TileDesc* __restrict__ tiles, uint32_t* __restrict__ seg_entry,
                uint32_t* __restrict__ seg_exit, uint32_t* __restrict__ seg_cd) {
-    __shared__ uint32_t s_pos[NCP][ENT_TPB];   // [j] = first block start >= seg_start + (j+1)*CP_BITS
+    __shared__ uint32_t s_pos[NCP][ENT_TPB];   // [j] = first block start >= seg_start + (j+1)*CP_BITS (f position)
     __shared__ uint32_t s_cd[NCP][ENT_TPB];    // blocks started before it | DC sum of them << 16
     __shared__ uint32_t s_rexit[ENT_TPB];      // resolved exits (round 1)
     const int t = threadIdx.x;
@@ -130,8 +148,10 @@ k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
     const int seg = (int)td.seg0 - 1 + t;
     const bool valid = seg >= 0 && seg < (int)sd.nseg;
     const uint8_t* base = payload + sd.byte_off;
-    const uint32_t total_bits = sd.byte_len * 8u;
-    const uint32_t seg_start = (uint32_t)seg * SEG_BITS, seg_end = seg_start + SEG_BITS;
+    const uint32_t bias = stream_bias(base);
+    const uint32_t ftotal = sd.byte_len * 8u + bias;
+    const uint32_t fstop_eos = eos_stop(ftotal);
+    const uint32_t seg_start = (uint32_t)seg * SEG_BITS + bias, seg_end = seg_start + SEG_BITS;
 
     // ---- speculative parse from the segment's first bit --------------------------------------------
     {
@@ -139,24 +159,23 @@ k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
         uint32_t cnt = 0;
         int dcsum = 0;
         uint32_t pos = seg_start;
-        bool active = valid && pos + MIN_BLOCK_BITS <= total_bits;
+        bool active = valid && pos < fstop_eos;
         Parser ps;
-        if (active) ps.start(base, seg_start, total_bits);
+        if (active) ps.start(base, seg_start, ftotal);
         uint32_t next_cp = seg_start + CP_BITS;
+        uint32_t next_stop = min(next_cp, fstop_eos);
         while (__any_sync(FULL_MASK, active)) {
             if (active) {
-                int e;
-                const bool end = ps.step(total_bits, e);
-                dcsum += e;
-                if (end) {
-                    cnt++;
-                    pos = ps.pos;
-                    if (pos >= next_cp) {
-                        const uint32_t rec = cnt | ((uint32_t)dcsum << 16);
-                        do { s_pos[j][t] = pos; s_cd[j][t] = rec; j++; next_cp += CP_BITS; } while (j < NCP && pos >= next_cp);
-                        if (j == NCP) active = false;
-                    }
-                    if (pos + MIN_BLOCK_BITS > total_bits) active = false;   // end of stream: no further block can start
+                Parser::Sym y;
+                const bool end = ps.step(ftotal, y);
+                dcsum += y.dc ? y.e : 0;
+                cnt += end ? 1u : 0u;
+                if (end && ps.fpos >= next_stop) {           // rare: a checkpoint boundary or the end of the stream passed
+                    pos = ps.fpos;
+                    const uint32_t rec = cnt | ((uint32_t)dcsum << 16);
+                    while (j < NCP && pos >= next_cp) { s_pos[j][t] = pos; s_cd[j][t] = rec; j++; next_cp += CP_BITS; }
+                    if (j == NCP || pos >= fstop_eos) active = false;   // end of stream: no further block can start
+                    next_stop = min(next_cp, fstop_eos);
                 }
             }
         }
@@ -169,21 +188,21 @@ k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
 
     // ---- round 1: entry = predecessor's speculative exit -------------------------------------------------
     const bool own = valid && t >= 1;
-    uint32_t E = (own && seg != 0) ? s_pos[NCP - 1][t - 1] : 0u;
-    Resolved rs = resolve_by_merge(base, E, seg_start, seg_end, total_bits, s_pos, s_cd, t, own);
+    uint32_t E = (own && seg != 0) ? s_pos[NCP - 1][t - 1] : bias;
+    Resolved rs = resolve_by_merge(base, E, seg_start, seg_end, ftotal, s_pos, s_cd, t, own);
     s_rexit[t] = own ? rs.exit_pos : (valid ? s_pos[NCP - 1][t] : 0u);   // the halo keeps its speculative exit
     __syncthreads();
     // ---- round 2: re-merge where the predecessor's resolved exit differs from its speculative one ----------
     {
         const uint32_t E2 = (own && seg != 0) ? s_rexit[t - 1] : E;
         const bool redo = own && E2 != E;
-        const Resolved r2 = resolve_by_merge(base, E2, seg_start, seg_end, total_bits, s_pos, s_cd, t, redo);
+        const Resolved r2 = resolve_by_merge(base, E2, seg_start, seg_end, ftotal, s_pos, s_cd, t, redo);
         if (redo) { E = E2; rs = r2; }
     }
     if (own) {
         const uint32_t g = sd.seg_base + (uint32_t)seg;
-        seg_entry[g] = E;
-        seg_exit[g] = rs.exit_pos;
+        seg_entry[g] = E - bias;
+        seg_exit[g] = rs.exit_pos - bias;
         seg_cd[g] = (rs.cnt & 0xFFFFu) | (rs.dc << 16);
     }
 }
@@ -199,7 +218,8 @@ k_entropy_chain(const uint8_t* __restrict__ payload, const StreamDesc* __restric
                 uint32_t* __restrict__ stream_blocks, unsigned long long* __restrict__ fixups) {
     const StreamDesc sd = streams[blockIdx.x];
     const uint8_t* base = payload + sd.byte_off;
-    const uint32_t total_bits = sd.byte_len * 8u;
+    const uint32_t bias = stream_bias(base);
+    const uint32_t ftotal = sd.byte_len * 8u + bias;
     volatile uint32_t* v_entry = seg_entry + sd.seg_base;
     volatile uint32_t* v_exit = seg_exit + sd.seg_base;
     volatile uint32_t* v_cd = seg_cd + sd.seg_base;
@@ -213,7 +233,7 @@ k_entropy_chain(const uint8_t* __restrict__ payload, const StreamDesc* __restric
             uint32_t E = i ? v_exit[i - 1] : 0u;
             if (v_entry[i] != E) {
                 uint32_t cnt, dc;
-                uint32_t x = parse_segment(base, E, (i + 1) * SEG_BITS, total_bits, cnt, dc);
+                uint32_t x = parse_segment(base, E + bias, (i + 1) * SEG_BITS + bias, ftotal, cnt, dc) - bias;
                 v_entry[i] = E;
                 v_exit[i] = x;
                 v_cd[i] = (cnt & 0xFFFFu) | (dc << 16);
@@ -277,7 +297,8 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
     const uint32_t seg = td.seg0 + (uint32_t)t;
     const bool valid = seg < sd.nseg;
     const uint8_t* base = payload + sd.byte_off;
-    const uint32_t total_bits = sd.byte_len * 8u;
+    const uint32_t bias = stream_bias(base);
+    const uint32_t ftotal = sd.byte_len * 8u + bias;
     const uint32_t g = sd.seg_base + (valid ? seg : 0u);
     const uint32_t first = valid ? seg_first[g] : 0u;
     const uint32_t cd = valid ? seg_cd[g] : 0u;
@@ -288,7 +309,7 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
     uint32_t o = o_base, o_blk = o_base;
     bool active = valid && cnt != 0;
     Parser ps;
-    if (active) ps.start(base, seg_entry[g], total_bits);
+    if (active) ps.start(base, seg_entry[g] + bias, ftotal);
     int cur = sd.ptype ? 0 : (int)(cd >> 16);
     const bool pframe = sd.ptype != 0;
     uint32_t k = 0;
@@ -297,7 +318,7 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
     while (__any_sync(FULL_MASK, active)) {
         if (active) {
             Parser::Sym y;
-            const bool end = ps.step(total_bits, y);
+            const bool end = ps.step(ftotal, y);
             if (y.dc) { cur = pframe ? y.e : cur + y.e; o_blk = o; }
             if (y.coded && y.at < 64u) {
 #pragma unroll
