@@ -64,7 +64,7 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     int rc;
     if ((rc = s_in.reserve(len + 64))) return rc;
     if ((rc = s_tab.reserve(256 + 256 + b_sync + b_write))) return rc;
-    if ((rc = s_seg.reserve((size_t)sd.nseg * 16 + 96))) return rc;
+    if ((rc = s_seg.reserve((size_t)sd.nseg * 20 + 96))) return rc;
     if ((rc = s_idx.reserve((size_t)num_blocks * 8 + (size_t)sd.nseg * SYM_STRIDE * 4 + 128))) return rc;
     if ((rc = s_mid.reserve(coef_bytes))) return rc;
     uint8_t* tab = s_tab.as<uint8_t>();
@@ -85,10 +85,11 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     j.stream_lo = 0; j.n_streams = 1;
     j.n_sync_tiles = (uint32_t)sync_tiles.size(); j.n_write_tiles = (uint32_t)write_tiles.size();
     uint32_t* seg = s_seg.as<uint32_t>();
-    j.d_seg_entry = seg; j.d_seg_exit = seg + sd.nseg; j.d_seg_cd = seg + 2 * (size_t)sd.nseg;
+    j.d_seg_entry = seg; j.d_seg_exit = seg + sd.nseg; j.d_seg_cnt = seg + 2 * (size_t)sd.nseg;
     j.d_seg_first = seg + 3 * (size_t)sd.nseg;
-    j.d_stream_blocks = seg + 4 * (size_t)sd.nseg;
-    j.d_fixups = reinterpret_cast<unsigned long long*>(seg + 4 * (size_t)sd.nseg + 2);
+    j.d_seg_dc = seg + 4 * (size_t)sd.nseg;
+    j.d_stream_blocks = seg + 5 * (size_t)sd.nseg;
+    j.d_fixups = reinterpret_cast<unsigned long long*>(seg + ((5 * (size_t)sd.nseg + 3) & ~(size_t)1));
     j.d_blk_info = s_idx.as<uint2>();
     j.d_sym = s_idx.as<uint32_t>() + ((2 * (size_t)num_blocks + 7) & ~(size_t)7);
     j.sym_seg0 = 0;

@@ -25,6 +25,10 @@ constexpr uint32_t MAX_STREAM_BYTES = 1u << 28; // bit positions are 32-bit
 // (zig-zag index | amplitude << 16) into a fixed-stride region.  A segment owns at most SEG_BITS/9 coded
 // symbols (>= 9 bits each) that start inside it plus the rest of its last block (<= 63 AC coefficients).
 constexpr uint32_t SYM_STRIDE = (SEG_BYTES * 8 / 9 + 63 + 7) / 8 * 8;   // entries per segment, a multiple of 8
+// Block index entry (uint2): .x = position of the block's first list entry -- always inside its segment's
+// region, so .x / SYM_STRIDE names the segment (whose DC predictor the decode kernels add) -- or BLK_NO_SEG
+// for a block the stream does not hold; .y = segment-relative DC level | list entries << 16.
+constexpr uint32_t BLK_NO_SEG = 0xFFFFFFFFu;
 
 // One plane bitstream of one frame (built by the host from the 16-byte frame headers,
 // LIB/decoder/mjpeg423_decoder.c:94-107).
@@ -79,6 +83,7 @@ struct Parser {
     uint32_t flim;         // the current block is ended at or after this f position
     uint32_t idx;          // zig-zag index of the next AC coefficient
     uint32_t nh;           // minus the header length of the next symbol: -4 = DC (a block start), -8 = AC
+    uint32_t rmask;        // 32 while live; 0 = PARKED: the window is never refilled again (see park())
 
     // fbits = f position to start at (a block start), ftotal = f position of the end of the stream.
     __device__ __forceinline__ void start(const uint8_t* base, uint32_t fbits, uint32_t ftotal) {
@@ -90,31 +95,44 @@ struct Parser {
         flim = min(fbits + RUNAWAY_BITS, ftotal);
         idx = 1;
         nh = (uint32_t)-4;
+        rmask = 32u;
     }
-    __device__ __forceinline__ bool at_block_start() const { return nh == (uint32_t)-4; }
+    // The passes run UNIFORM loops: every lane of the warp steps every iteration, and a lane with nothing
+    // (more) to parse is parked instead of branching around the step -- it keeps stepping through an all-zero
+    // window (DC size 0 / END symbols: no coefficient, 4 or 8 bits each) without ever touching memory again,
+    // and the pass ignores what it returns.
+    __device__ __forceinline__ void park() { rmask = 0u; w0 = 0u; w1 = 0u; }
+    __device__ __forceinline__ void init_parked() {
+        wp = nullptr; w0 = w1 = 0u; fpos = 0u; flim = 0u; idx = 1u; nh = (uint32_t)-4; rmask = 0u;
+    }
 
     // What the last step() consumed.
     struct Sym {
         bool dc;           // it was the block's DC symbol
         bool coded;        // it was a non-zero AC coefficient ...
         uint32_t at;       // ... at this zig-zag index (may be >= 64 on non-conforming input: ignore then)
-        int e;             // amplitude of the DC / coded AC coefficient (HUFF_EXTEND, :204); 0 for a size-0 DC symbol,
-                           // unspecified for END / ZRL
+        int e;             // WANT_E only: amplitude of the DC / coded AC coefficient (HUFF_EXTEND, :204); 0 for a
+                           // size-0 DC symbol, unspecified for END / ZRL
     };
     // Consume one symbol.  Returns true when it ended the block (the parser is then positioned on the
-    // next block's DC symbol).  WANT_E = false skips the amplitude of AC symbols (sym.e valid for DC only).
+    // next block's DC symbol).
+    template <bool WANT_E>
     __device__ __forceinline__ bool step(uint32_t ftotal, Sym& sym) {
         const uint32_t t = __funnelshift_l(w1, w0, fpos);               // next 32 stream bits
         const bool dc = nh == (uint32_t)-4;
         const uint32_t rs = __funnelshift_r(t, 0u, nh);                 // t >> (32 - header bits): the 4 / 8 header bits
         const uint32_t size = rs & 15u, run = rs >> 4;                  // run == 0 for a DC symbol (rs < 16)
         const uint32_t fnew = fpos + size - nh;
-        // amplitude: the `size` bits after the header, JPEG VLI sign extension (HUFF_EXTEND): a field whose top
-        // bit is clear stands for field - 2^size + 1.  size 0 gives 0.
-        const uint32_t v = t << (0u - nh);
-        const uint32_t amp = (v >> 1) >> (31u ^ size);
-        const int e = (int)amp + (((int)v >= 0) ? (int)(0xFFFFFFFFu << size) + 1 : 0);
-        if ((fpos ^ fnew) & 32u) {                                      // crossed into w1: fetch the word after it
+        if (WANT_E) {
+            // amplitude: the `size` bits after the header, JPEG VLI sign extension (HUFF_EXTEND): a field whose
+            // top bit is clear stands for field - 2^size + 1.  size 0 gives 0.
+            const uint32_t v = t << (0u - nh);
+            const uint32_t amp = (v >> 1) >> (31u ^ size);
+            sym.e = (int)amp + (((int)v >= 0) ? (int)(0xFFFFFFFFu << size) + 1 : 0);
+        } else {
+            sym.e = 0;
+        }
+        if ((fpos ^ fnew) & rmask) {                                    // crossed into w1: fetch the word after it
             w0 = w1;
             w1 = __byte_perm(__ldg(wp), 0, 0x0123);
             wp++;
@@ -130,7 +148,6 @@ struct Parser {
         sym.dc = dc;
         sym.coded = coded;
         sym.at = at;
-        sym.e = e;
         return end;
     }
 };

@@ -51,11 +51,19 @@ __device__ __forceinline__ void load_slot_rows(const uint8_t* smem, int t, uint4
     for (int r = 0; r < 8; r++) rows[r] = *reinterpret_cast<const uint4*>(smem + t * 128 + ((r ^ (t & 7)) << 4));
 }
 
+// Block index entry -> .y with the DC level made absolute: adds the DC predictor entering the block's segment
+// (k_entropy_dcscan; zero for P frames, whose DC symbols are deltas against the previous frame).
+__device__ __forceinline__ uint32_t absolute_dc(uint2 info, const uint32_t* __restrict__ seg_dc) {
+    const uint32_t pred = info.x == BLK_NO_SEG ? 0u : __ldg(seg_dc + info.x / SYM_STRIDE);
+    return (info.y & 0xFFFF0000u) | ((info.y + pred) & 0xFFFFu);
+}
+
 // ---- coefficient planes ------------------------------------------------------------------------------
 // grid = (ceil(nb / 128), number of streams in `stream_ids`).
 __global__ void __launch_bounds__(DEC_TPB)
 k_decode_coef(const StreamDesc* __restrict__ streams, const uint32_t* __restrict__ stream_ids,
-              const uint2* __restrict__ blk_info, const uint32_t* __restrict__ sym, const int16_t* __restrict__ quant, int16_t* coef) {
+              const uint2* __restrict__ blk_info, const uint32_t* __restrict__ sym, const uint32_t* __restrict__ seg_dc,
+              const int16_t* __restrict__ quant, int16_t* coef) {
     __shared__ __align__(128) uint8_t slots[DEC_TPB * 128];
     __shared__ uint32_t s_zq[64];
     const int t = threadIdx.x;
@@ -79,7 +87,7 @@ k_decode_coef(const StreamDesc* __restrict__ streams, const uint32_t* __restrict
     if ((uint32_t)t < nblk) {
         const uint32_t gb = sd.block_base + b0 + (uint32_t)t;
         const uint2 info = __ldg(blk_info + gb);
-        const uint32_t meta = info.y;
+        const uint32_t meta = absolute_dc(info, seg_dc);
         const uint32_t* src = sym + info.x;
         const uint32_t n = meta >> 16;
         const int dc = (int)(int16_t)(meta & 0xFFFFu);
@@ -126,7 +134,7 @@ constexpr int FUSED_SMEM = FUSED_TPB * (256 + 128) + 2 * 64 * 4;
 
 __global__ void __launch_bounds__(FUSED_TPB, 1)
 k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__ blk_info,
-               const uint32_t* __restrict__ sym,
+               const uint32_t* __restrict__ sym, const uint32_t* __restrict__ seg_dc,
                const int16_t* __restrict__ quant, uint8_t* __restrict__ out, uint32_t nb, uint32_t wb, uint32_t W,
                uint32_t n_frames) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -160,9 +168,9 @@ k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__
         const uint32_t* lst[3];
 #pragma unroll
         for (int p = 0; p < 3; p++) {
-            const uint2 info = live ? __ldg(blk_info + sd0[p].block_base + b) : make_uint2(0u, 0u);
+            const uint2 info = live ? __ldg(blk_info + sd0[p].block_base + b) : make_uint2(BLK_NO_SEG, 0u);
             lst[p] = sym + info.x;
-            meta[p] = info.y;
+            meta[p] = absolute_dc(info, seg_dc);
         }
 #pragma unroll
         for (int p = 0; p < 3; p++)
@@ -282,7 +290,8 @@ cudaError_t launch_decode_coef(const EntropyJob& j, const uint32_t* d_stream_ids
                                const int16_t* d_quant, int16_t* d_coef, cudaStream_t s) {
     if (n_ids == 0 || nb == 0) return cudaSuccess;
     dim3 grid((nb + DEC_TPB - 1) / DEC_TPB, n_ids);
-    k_decode_coef<<<grid, DEC_TPB, 0, s>>>(j.d_streams, d_stream_ids, j.d_blk_info, j.d_sym, d_quant, d_coef);
+    k_decode_coef<<<grid, DEC_TPB, 0, s>>>(j.d_streams, d_stream_ids, j.d_blk_info, j.d_sym, j.d_seg_dc + j.sym_seg0,
+                                           d_quant, d_coef);
     return cudaGetLastError();
 }
 cudaError_t launch_decode_fused(const EntropyJob& j, const int16_t* d_quant, void* d_out, uint32_t n_frames,
@@ -301,7 +310,7 @@ cudaError_t launch_decode_fused(const EntropyJob& j, const int16_t* d_quant, voi
     const uint64_t want = (n_tiles + FUSED_TPB / 32 - 1) / (FUSED_TPB / 32);
     const unsigned grid = (unsigned)(want < (uint64_t)n_sm ? want : (uint64_t)n_sm);     // persistent: one CTA per SM
     k_decode_fused<<<grid, FUSED_TPB, FUSED_SMEM, s>>>(j.d_streams + j.stream_lo, j.d_blk_info, j.d_sym,
-                                                       d_quant, (uint8_t*)d_out, nb, wb, W, n_frames);
+                                                       j.d_seg_dc + j.sym_seg0, d_quant, (uint8_t*)d_out, nb, wb, W, n_frames);
     return cudaGetLastError();
 }
 

@@ -264,7 +264,7 @@ namespace {
 
 struct Tables {           // device addresses inside ctx->tables / ctx->segs
     StreamDesc* streams; TileDesc* sync_tiles; TileDesc* write_tiles;
-    uint32_t *seg_entry, *seg_exit, *seg_cd, *seg_first, *stream_blocks;
+    uint32_t *seg_entry, *seg_exit, *seg_cnt, *seg_first, *seg_dc, *stream_blocks;
     unsigned long long* fixups;
 };
 
@@ -283,10 +283,11 @@ Tables tables_of(mjpeg423_b200_ctx* c, const Plan& plan) {
     uint8_t* sb = c->segs.as<uint8_t>();
     t.seg_entry = reinterpret_cast<uint32_t*>(sb);
     t.seg_exit = reinterpret_cast<uint32_t*>(sb + b_seg);
-    t.seg_cd = reinterpret_cast<uint32_t*>(sb + 2 * b_seg);
+    t.seg_cnt = reinterpret_cast<uint32_t*>(sb + 2 * b_seg);
     t.seg_first = reinterpret_cast<uint32_t*>(sb + 3 * b_seg);
-    t.stream_blocks = reinterpret_cast<uint32_t*>(sb + 4 * b_seg);
-    t.fixups = reinterpret_cast<unsigned long long*>(sb + 4 * b_seg + b_sb);
+    t.seg_dc = reinterpret_cast<uint32_t*>(sb + 4 * b_seg);
+    t.stream_blocks = reinterpret_cast<uint32_t*>(sb + 5 * b_seg);
+    t.fixups = reinterpret_cast<unsigned long long*>(sb + 5 * b_seg + b_sb);
     return t;
 }
 
@@ -298,7 +299,7 @@ int upload_tables(mjpeg423_b200_ctx* c, const Plan& plan, Tables& t, cudaStream_
     int rc = c->tables.reserve(b_streams + b_sync + b_write + 256);
     if (rc) return rc;
     const size_t nseg = plan.f_seg0.empty() ? 0 : plan.f_seg0.back();
-    rc = c->segs.reserve(4 * align256(nseg * 4) + align256(plan.streams.size() * 4) + 256);   // ... + 2 x u64 counters
+    rc = c->segs.reserve(5 * align256(nseg * 4) + align256(plan.streams.size() * 4) + 256);   // ... + 2 x u64 counters
     if (rc) return rc;
     t = tables_of(c, plan);
     CU(cudaMemcpyAsync(t.streams, plan.streams.data(), plan.streams.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, s));
@@ -369,7 +370,8 @@ EntropyJob make_job(const Plan& plan, const Tables& t, const uint8_t* d_payload_
     j.stream_lo = f0 * 3; j.n_streams = (f1 - f0) * 3;
     j.n_sync_tiles = plan.f_sync0[f1] - plan.f_sync0[f0];
     j.n_write_tiles = plan.f_write0[f1] - plan.f_write0[f0];
-    j.d_seg_entry = t.seg_entry; j.d_seg_exit = t.seg_exit; j.d_seg_cd = t.seg_cd; j.d_seg_first = t.seg_first;
+    j.d_seg_entry = t.seg_entry; j.d_seg_exit = t.seg_exit; j.d_seg_cnt = t.seg_cnt; j.d_seg_first = t.seg_first;
+    j.d_seg_dc = t.seg_dc;
     j.d_stream_blocks = t.stream_blocks; j.d_fixups = t.fixups;
     // StreamDesc.block_base is plan-relative: shift the chunk buffers back by the chunk's first block
     // ... and StreamDesc.seg_base too: same for the symbol lists
@@ -397,7 +399,7 @@ int enqueue_chunk(mjpeg423_b200_ctx* c, const Plan& plan, const Tables& t, const
     if (prof) CU(cudaEventRecord(prof[2], s));
     CU(launch_entropy_index(j, s));
     if (prof) CU(cudaEventRecord(prof[3], s));
-    c->stats.kernel_launches += 3;
+    c->stats.kernel_launches += 4;
     if (mode == 0) {
         CU(launch_decode_fused(j, c->d_quant, d_out, f1 - f0, plan.W, plan.H, s));
         c->stats.kernel_launches += 1;
@@ -565,7 +567,7 @@ extern "C" int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* c, int16_t* d_c
         c->stats.kernel_launches += 1;
     }
     CU(cudaEventRecord(e[4], s));
-    c->stats.kernel_launches += 3;
+    c->stats.kernel_launches += 4;
     rc = finish_stats(c, plan, t, s);
     CU(cudaEventElapsedTime(&c->stats.total_ms, e[0], e[4]));
     CU(cudaEventElapsedTime(&c->stats.sync_ms, e[0], e[1]));

@@ -22,7 +22,8 @@ struct EntropyJob {
     const TileDesc* d_write_tiles = nullptr;     // first write tile of the chunk
     uint32_t stream_lo = 0, n_streams = 0;       // streams of the chunk (chain kernel: one CTA each)
     uint32_t n_sync_tiles = 0, n_write_tiles = 0;
-    uint32_t *d_seg_entry = nullptr, *d_seg_exit = nullptr, *d_seg_cd = nullptr, *d_seg_first = nullptr; // plan-wide
+    uint32_t *d_seg_entry = nullptr, *d_seg_exit = nullptr, *d_seg_cnt = nullptr, *d_seg_first = nullptr; // plan-wide
+    uint32_t* d_seg_dc = nullptr;                // plan-wide: DC total, then DC predictor, of every segment
     uint32_t* d_stream_blocks = nullptr;         // plan-wide, per stream
     unsigned long long* d_fixups = nullptr;
     uint2* d_blk_info = nullptr;                 // block index, addressed by StreamDesc.block_base + b
