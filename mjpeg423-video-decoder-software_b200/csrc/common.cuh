@@ -163,12 +163,13 @@ constexpr uint32_t FULL_MASK = 0xFFFFFFFFu;
 template <int SHIFT>
 __device__ __forceinline__ void idct8(int i0, int i1, int i2, int i3, int i4, int i5, int i6, int i7,
                                       int (&o)[8]) {
-    constexpr int RND = 1 << (SHIFT - 1);   // DESCALE, dct_math.h:48
+    constexpr int RND = 1 << (SHIFT - 1);   // DESCALE, dct_math.h:48 -- added once to the even part (wrap-around
+                                            // int32 sums are associative), not to each of the 8 outputs
     int z1 = (i2 + i6) * 4433;
     int tmp2 = z1 + i6 * -15137;
     int tmp3 = z1 + i2 * 6270;
-    int tmp0 = (int)((unsigned)(i0 + i4) << 13);
-    int tmp1 = (int)((unsigned)(i0 - i4) << 13);
+    int tmp0 = (int)(((unsigned)(i0 + i4) << 13) + (unsigned)RND);
+    int tmp1 = (int)(((unsigned)(i0 - i4) << 13) + (unsigned)RND);
     int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
     int a0 = i7, a1 = i5, a2 = i3, a3 = i1;
     int y1 = a0 + a3, y2 = a1 + a2, y3 = a0 + a2, y4 = a1 + a3;
@@ -178,20 +179,28 @@ __device__ __forceinline__ void idct8(int i0, int i1, int i2, int i3, int i4, in
     y3 = y3 * -16069 + y5;
     y4 = y4 * -3196 + y5;
     a0 += y1 + y3; a1 += y2 + y4; a2 += y2 + y3; a3 += y1 + y4;
-    o[0] = (tmp10 + a3 + RND) >> SHIFT;
-    o[7] = (tmp10 - a3 + RND) >> SHIFT;
-    o[1] = (tmp11 + a2 + RND) >> SHIFT;
-    o[6] = (tmp11 - a2 + RND) >> SHIFT;
-    o[2] = (tmp12 + a1 + RND) >> SHIFT;
-    o[5] = (tmp12 - a1 + RND) >> SHIFT;
-    o[3] = (tmp13 + a0 + RND) >> SHIFT;
-    o[4] = (tmp13 - a0 + RND) >> SHIFT;
+    o[0] = (tmp10 + a3) >> SHIFT;
+    o[7] = (tmp10 - a3) >> SHIFT;
+    o[1] = (tmp11 + a2) >> SHIFT;
+    o[6] = (tmp11 - a2) >> SHIFT;
+    o[2] = (tmp12 + a1) >> SHIFT;
+    o[5] = (tmp12 - a1) >> SHIFT;
+    o[3] = (tmp13 + a0) >> SHIFT;
+    o[4] = (tmp13 - a0) >> SHIFT;
 }
 
 __device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xFFFFu); }
 __device__ __forceinline__ int hi16(uint32_t w) { return (int)w >> 16; }
 // NORMALIZE, idct.c:20: max(min(v, 255), 0) -- one VIMNMX.RELU.
 __device__ __forceinline__ uint32_t clamp255(int v) { return (uint32_t)__vimin_s32_relu(v, 255); }
+
+// Four int32 -> four bytes, each clamped to 0..255 (NORMALIZE, idct.c:20), v0 in the low byte: two I2IP.U8.S32.SAT.
+__device__ __forceinline__ uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3) {
+    uint32_t hi, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(v3), "r"(v2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(hi));
+    return d;
+}
 
 // Column occupancy of a block held as 8 rows of packed int16: bit c of `ac` is set when column c has a
 // non-zero coefficient in rows 1..7, bit c of `any` when it has one in any row.
@@ -256,8 +265,8 @@ __device__ __forceinline__ void idct_block(const uint4 (&rows)[8], uint32_t acma
         int o[8];
         if (low_half_only) idct8<18>(ws[r][0], ws[r][1], ws[r][2], ws[r][3], 0, 0, 0, 0, o);
         else idct8<18>(ws[r][0], ws[r][1], ws[r][2], ws[r][3], ws[r][4], ws[r][5], ws[r][6], ws[r][7], o);
-        out[2 * r] = clamp255(o[0]) | (clamp255(o[1]) << 8) | (clamp255(o[2]) << 16) | (clamp255(o[3]) << 24);
-        out[2 * r + 1] = clamp255(o[4]) | (clamp255(o[5]) << 8) | (clamp255(o[6]) << 16) | (clamp255(o[7]) << 24);
+        out[2 * r] = pack4_sat_u8(o[0], o[1], o[2], o[3]);
+        out[2 * r + 1] = pack4_sat_u8(o[4], o[5], o[6], o[7]);
     }
 }
 
@@ -286,33 +295,36 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
                  : "memory");
 }
 
-// Colour conversion of pixels that share one (Cb, Cr) pair -- a block whose chroma blocks are flat.
+// ---- packed colour conversion -----------------------------------------------------------------------------
 // Because Y << 14 has no low bits, NORMALIZE_RGB((Y << 14) + k) == clamp(Y + (k >> 14), 0, 255) exactly
-// (arithmetic shift = floor; k = the chroma terms of ycbcr_to_rgb.c:33-37, per-block constants here, |k >> 14| < 256).
-// Two pixels are processed per register in signed 16-bit lanes, biased by 256 so that the packed add never
-// borrows across lanes: lane = Y + K + 256, clamped to [256, 511] with two VIMNMX.S16x2; the low byte of each
-// lane is the result and the high byte (always 1, msb clear) provides the zero alpha through PRMT's sign mode.
+// (arithmetic shift = floor; k = the chroma terms of ycbcr_to_rgb.c:33-37, |k >> 14| < 256).  Two pixels are
+// processed per register in signed 16-bit lanes: one VIADDMNMX.S16x2.RELU does the add and both clamps of a
+// channel for two pixels, and PRMT assembles the BGRA words (alpha = the zero high byte of a lane).
+// Chroma terms are computed x4 in 32 bits, so that floor(k / 2^14) is the HIGH half of the product and one
+// PRMT packs two of them.
+__device__ __forceinline__ uint32_t addclamp2(uint32_t y2, uint32_t k2) { return __viaddmin_s16x2_relu(y2, k2, 0x00FF00FFu); }
+__device__ __forceinline__ void bgra2(uint32_t b, uint32_t g, uint32_t r, uint32_t& p0, uint32_t& p1) {
+    const uint32_t bg = __byte_perm(b, g, 0x6240);       // B0 G0 B1 G1
+    p0 = __byte_perm(bg, r, 0x5410);                     // B0 G0 R0 0
+    p1 = __byte_perm(bg, r, 0x7632);                     // B1 G1 R1 0
+}
+__device__ __forceinline__ int kr4(uint32_t cr) { return 4 * 22970 * (int)cr - 4 * 128 * 22970; }
+__device__ __forceinline__ int kb4(uint32_t cb) { return 4 * 29032 * (int)cb - 4 * 128 * 29032; }
+__device__ __forceinline__ int kg4(uint32_t cb, uint32_t cr) {
+    return -4 * 5638 * (int)cb - 4 * 11700 * (int)cr + 4 * 128 * (5638 + 11700);
+}
+__device__ __forceinline__ uint32_t hi2(int a0, int a1) { return __byte_perm((uint32_t)a0, (uint32_t)a1, 0x7632); }   // a0 >> 16 | a1 >> 16 << 16
+
+// Pixels that share one (Cb, Cr) pair -- a block whose chroma blocks are flat: the chroma terms are per-block constants.
 struct FlatChroma {
     uint32_t kr2, kg2, kb2;
     __device__ __forceinline__ FlatChroma(uint32_t cb, uint32_t cr) {
-        const int cbb = (int)cb - 128, crr = (int)cr - 128;
-        kr2 = (uint32_t)(((22970 * crr) >> 14) + 256) * 0x00010001u;
-        kg2 = (uint32_t)(((-5638 * cbb - 11700 * crr) >> 14) + 256) * 0x00010001u;
-        kb2 = (uint32_t)(((29032 * cbb) >> 14) + 256) * 0x00010001u;
+        const int r = kr4(cr), g = kg4(cb, cr), b = kb4(cb);
+        kr2 = hi2(r, r); kg2 = hi2(g, g); kb2 = hi2(b, b);
     }
-    // PRMT with the selector's sign-replicate bit (bit 3 of a nibble); __byte_perm() masks that bit off.
-    static __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-        uint32_t d;
-        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-        return d;
-    }
-    static __device__ __forceinline__ uint32_t clamp2(uint32_t x) { return __vmaxs2(__vmins2(x, 0x01FF01FFu), 0x01000100u); }
     // y2 = two Y samples in 16-bit lanes -> two BGRA words
     __device__ __forceinline__ void px2(uint32_t y2, uint32_t& p0, uint32_t& p1) const {
-        const uint32_t r = clamp2(y2 + kr2), g = clamp2(y2 + kg2), b = clamp2(y2 + kb2);
-        const uint32_t bg = __byte_perm(b, g, 0x6240);       // B0 G0 B1 G1
-        p0 = prmt(bg, r, 0xD410);                            // B0 G0 R0 0
-        p1 = prmt(bg, r, 0xF632);                            // B1 G1 R1 0
+        bgra2(addclamp2(y2, kb2), addclamp2(y2, kg2), addclamp2(y2, kr2), p0, p1);
     }
     __device__ __forceinline__ void row_store(uint32_t y0, uint32_t y1, uint8_t* dst) const {
         uint32_t v[8];
@@ -324,15 +336,27 @@ struct FlatChroma {
     }
 };
 
+// Four pixels (one packed word of each plane) -> four BGRA words.
+__device__ __forceinline__ void colour4(uint32_t y, uint32_t cb, uint32_t cr, uint32_t* v) {
+    uint32_t b[4], r[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { b[k] = __byte_perm(cb, 0, 0x4440 + k); r[k] = __byte_perm(cr, 0, 0x4440 + k); }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t y2 = __byte_perm(y, 0, h ? 0x4342 : 0x4140);
+        const uint32_t kr2 = hi2(kr4(r[2 * h]), kr4(r[2 * h + 1]));
+        const uint32_t kg2 = hi2(kg4(b[2 * h], r[2 * h]), kg4(b[2 * h + 1], r[2 * h + 1]));
+        const uint32_t kb2 = hi2(kb4(b[2 * h]), kb4(b[2 * h + 1]));
+        bgra2(addclamp2(y2, kb2), addclamp2(y2, kg2), addclamp2(y2, kr2), v[2 * h], v[2 * h + 1]);
+    }
+}
+
 // One block row (8 pixels) of Y/Cb/Cr packed samples -> 8 BGRA words, stored as one 32-byte sector.
 __device__ __forceinline__ void colour_row_store(uint32_t y0, uint32_t y1, uint32_t cb0, uint32_t cb1, uint32_t cr0,
                                                  uint32_t cr1, uint8_t* dst) {
     uint32_t v[8];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        v[k] = ycc_to_bgra((y0 >> (8 * k)) & 255u, (cb0 >> (8 * k)) & 255u, (cr0 >> (8 * k)) & 255u);
-        v[4 + k] = ycc_to_bgra((y1 >> (8 * k)) & 255u, (cb1 >> (8 * k)) & 255u, (cr1 >> (8 * k)) & 255u);
-    }
+    colour4(y0, cb0, cr0, v);
+    colour4(y1, cb1, cr1, v + 4);
     st_global_v8(dst, v);
 }
 

@@ -130,7 +130,7 @@ k_decode_coef(const StreamDesc* __restrict__ streams, const uint32_t* __restrict
 //                          pass 1 reads a column with one LDS.128.)
 //   stash words [32][T]    word p*16 + 2r + h = samples of plane p (Y, Cb), row r, half h
 constexpr int FUSED_TPB = 576;                                   // 18 warps x 384 B/thread = 216 KB of the SM's 227 KB
-constexpr int FUSED_SMEM = FUSED_TPB * (256 + 128) + 2 * 64 * 4;
+constexpr int FUSED_SMEM = FUSED_TPB * (256 + 128) + 2 * 64 * 8;
 
 __global__ void __launch_bounds__(FUSED_TPB, 1)
 k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__ blk_info,
@@ -141,12 +141,13 @@ k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__
     uint4* s_ws = reinterpret_cast<uint4*>(smem);                                   // granules 0..15
     uint8_t* s_coef = smem + 8 * FUSED_TPB * 16;                                    // granules 8..15
     uint32_t* s_stash = reinterpret_cast<uint32_t*>(smem + FUSED_TPB * 256);
-    uint32_t* s_zq = reinterpret_cast<uint32_t*>(smem + FUSED_TPB * 384);           // 2 x 64 words
+    uint2* s_zq = reinterpret_cast<uint2*>(smem + FUSED_TPB * 384);                 // 2 x 64 entries
     const int t = threadIdx.x;
-    if (t < 128) {                                                       // zig-zag -> transposed offset | quant
+    if (t < 128) {     // zig-zag index -> .x = transposed slot offset | quant << 16, .y = column bit | (row >= 1) column bit << 8
         const int tab = t >> 6, k = t & 63;
-        const uint32_t n = c_zigzag[k];
-        s_zq[t] = ((n & 7u) * (FUSED_TPB * 16u) + (n >> 3) * 2u) | ((uint32_t)(uint16_t)quant[tab * 64 + n] << 16);
+        const uint32_t n = c_zigzag[k], col = n & 7u, row = n >> 3;
+        s_zq[t] = make_uint2((col * (FUSED_TPB * 16u) + row * 2u) | ((uint32_t)(uint16_t)quant[tab * 64 + n] << 16),
+                             (1u << col) | ((row ? 1u : 0u) << (8 + col)));
     }
     __syncthreads();
     uint8_t* my_coef = s_coef + t * 16;
@@ -186,17 +187,14 @@ k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__
             // (p is a loop variable: select the pre-fetched registers without dynamic indexing)
             const uint32_t pmeta = p == 0 ? meta[0] : p == 1 ? meta[1] : meta[2];
             const uint32_t* src = p == 0 ? lst[0] : p == 1 ? lst[1] : lst[2];
-            const uint32_t* zq = s_zq + (p ? 64 : 0);
+            const uint2* zq = s_zq + (p ? 64 : 0);
             const uint32_t n = pmeta >> 16;
-            *reinterpret_cast<int16_t*>(my_coef) = (int16_t)((int)(int16_t)(pmeta & 0xFFFFu) * (int)(zq[0] >> 16));  // lossless_decode.c:94-95
-            uint32_t m_ac = 0, m_any = 1u;
+            *reinterpret_cast<int16_t*>(my_coef) = (int16_t)((int)(int16_t)(pmeta & 0xFFFFu) * (int)(zq[0].x >> 16));  // lossless_decode.c:94-95
+            uint32_t m_bits = 1u;                                         // column 0 always holds the DC coefficient
             auto put = [&](uint32_t ent) {                                // dequantise + scatter one entry (:125)
-                const uint32_t z = zq[ent & 63u];
-                const uint32_t o = z & 0xFFFFu;                           // column * (T*16) + row * 2
-                *reinterpret_cast<int16_t*>(my_coef + o) = (int16_t)(((int)ent >> 16) * (int)(z >> 16));
-                const uint32_t col = o / (FUSED_TPB * 16u);
-                m_any |= 1u << col;
-                if (o & 15u) m_ac |= 1u << col;                           // row >= 1
+                const uint2 z = zq[ent & 63u];
+                *reinterpret_cast<int16_t*>(my_coef + (z.x & 0xFFFFu)) = (int16_t)(((int)ent >> 16) * (int)(z.x >> 16));
+                m_bits |= z.y;
             };
 #pragma unroll
             for (int i = 0; i < PRE; i++) {
@@ -211,7 +209,8 @@ k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__
                 if (i + 1 < n) put(e1);
             }
             __syncwarp();
-            const uint32_t acm = warp_or(m_ac), anym = warp_or(m_any);    // warp-uniform from here on
+            const uint32_t m_all = warp_or(m_bits);                       // warp-uniform from here on
+            const uint32_t acm = m_all >> 8, anym = m_all & 0xFFu;
 
             // emit(r, w0, w1): Y and Cb rows go to the stash, a Cr row completes 8 pixels.
             auto emit = [&](int r, uint32_t w0, uint32_t w1) {
@@ -278,8 +277,7 @@ k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__
                 } else {
                     idct8<18>((int)a.x, (int)a.y, (int)bq.x, (int)bq.y, 0, 0, 0, 0, o);
                 }
-                emit(r, clamp255(o[0]) | (clamp255(o[1]) << 8) | (clamp255(o[2]) << 16) | (clamp255(o[3]) << 24),
-                     clamp255(o[4]) | (clamp255(o[5]) << 8) | (clamp255(o[6]) << 16) | (clamp255(o[7]) << 24));
+                emit(r, pack4_sat_u8(o[0], o[1], o[2], o[3]), pack4_sat_u8(o[4], o[5], o[6], o[7]));
             }
         }
     }
