@@ -133,7 +133,7 @@ constexpr int FUSED_TPB = 576;                                   // 18 warps x 3
 constexpr int FUSED_SMEM = FUSED_TPB * (256 + 128) + 2 * 64 * 8;
 
 __global__ void __launch_bounds__(FUSED_TPB, 1)
-k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__ blk_info,
+k_decode_fused(const uint2* __restrict__ blk_info,
                const uint32_t* __restrict__ sym, const uint32_t* __restrict__ seg_dc,
                const int16_t* __restrict__ quant, uint8_t* __restrict__ out, uint32_t nb, uint32_t wb, uint32_t W,
                uint32_t n_frames) {
@@ -155,28 +155,45 @@ k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__
     const uint32_t n_tiles = tiles_per_frame * n_frames;
     const uint32_t warps_per_cta = FUSED_TPB / 32;
 
-    for (uint32_t tile = blockIdx.x * warps_per_cta + (uint32_t)(t >> 5); tile < n_tiles; tile += gridDim.x * warps_per_cta) {
+    // Block index entries (blk_info is the chunk's table: plane p of frame f starts at (f * 3 + p) * nb) are
+    // fetched one tile AHEAD, so that a tile starts with its list addresses known and only one load latency
+    // (the lists) is exposed instead of two dependent ones.
+    const uint32_t tile_step = gridDim.x * warps_per_cta;
+    auto load_info = [&](uint32_t tile_, uint2 (&inf)[3]) {
+        const uint32_t f_ = tile_ / tiles_per_frame;
+        const uint32_t b_ = (tile_ - f_ * tiles_per_frame) * 32u + (uint32_t)(t & 31);
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+            inf[p] = (tile_ < n_tiles && b_ < nb) ? __ldg(blk_info + (size_t)(f_ * 3u + p) * nb + b_) : make_uint2(BLK_NO_SEG, 0u);
+    };
+    uint2 ninfo[3];
+    uint32_t tile = blockIdx.x * warps_per_cta + (uint32_t)(t >> 5);
+    load_info(tile, ninfo);
+
+    for (; tile < n_tiles; tile += tile_step) {
         const uint32_t f = tile / tiles_per_frame;
         const uint32_t b = (tile - f * tiles_per_frame) * 32u + (uint32_t)(t & 31);
         const bool live = b < nb;
-        const StreamDesc* sd0 = streams + (size_t)f * 3;
         uint8_t* dst = out + ((size_t)f * nb * 64 + ((size_t)(b / wb) * 8 * W + (size_t)(b % wb) * 8)) * 4;
 
-        // Fetch the index entries of all three planes and the first PRE list entries of each up front:
-        // 3 + 3*PRE independent loads in flight per lane instead of a dependent load per coefficient.
-        constexpr int PRE = 4;
-        uint32_t meta[3], pre[3][PRE];
+        // The first PRE list entries of each plane (luminance blocks hold most of the coefficients) are fetched up
+        // front: independent loads in flight per lane instead of a dependent load per coefficient.  Entries past
+        // the end of a list read as 0 = "coefficient 0, amplitude 0": scattering one only clears the DC slot, which
+        // is written afterwards.
+        constexpr int PRE_Y = 8, PRE_C = 2;
+        uint32_t meta[3], preY[PRE_Y], preC[2][PRE_C];
         const uint32_t* lst[3];
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
-            const uint2 info = live ? __ldg(blk_info + sd0[p].block_base + b) : make_uint2(BLK_NO_SEG, 0u);
-            lst[p] = sym + info.x;
-            meta[p] = absolute_dc(info, seg_dc);
-        }
+        for (int p = 0; p < 3; p++) lst[p] = sym + ninfo[p].x;
 #pragma unroll
-        for (int p = 0; p < 3; p++)
+        for (int i = 0; i < PRE_Y; i++) preY[i] = (uint32_t)i < (ninfo[0].y >> 16) ? __ldg(lst[0] + i) : 0u;
 #pragma unroll
-            for (int i = 0; i < PRE; i++) pre[p][i] = (uint32_t)i < (meta[p] >> 16) ? __ldg(lst[p] + i) : 0u;
+        for (int p = 1; p < 3; p++)
+#pragma unroll
+            for (int i = 0; i < PRE_C; i++) preC[p - 1][i] = (uint32_t)i < (ninfo[p].y >> 16) ? __ldg(lst[p] + i) : 0u;
+#pragma unroll
+        for (int p = 0; p < 3; p++) meta[p] = absolute_dc(ninfo[p], seg_dc);
+        load_info(tile + tile_step, ninfo);
 
         bool cb_flat = false;                                            // warp-uniform: every Cb block of the tile is DC-only
 #pragma unroll 1
@@ -189,25 +206,33 @@ k_decode_fused(const StreamDesc* __restrict__ streams, const uint2* __restrict__
             const uint32_t* src = p == 0 ? lst[0] : p == 1 ? lst[1] : lst[2];
             const uint2* zq = s_zq + (p ? 64 : 0);
             const uint32_t n = pmeta >> 16;
-            *reinterpret_cast<int16_t*>(my_coef) = (int16_t)((int)(int16_t)(pmeta & 0xFFFFu) * (int)(zq[0].x >> 16));  // lossless_decode.c:94-95
             uint32_t m_bits = 1u;                                         // column 0 always holds the DC coefficient
             auto put = [&](uint32_t ent) {                                // dequantise + scatter one entry (:125)
                 const uint2 z = zq[ent & 63u];
                 *reinterpret_cast<int16_t*>(my_coef + (z.x & 0xFFFFu)) = (int16_t)(((int)ent >> 16) * (int)(z.x >> 16));
                 m_bits |= z.y;
             };
+            uint32_t i0;                                                  // entries scattered from the registers
+            if (p == 0) {
 #pragma unroll
-            for (int i = 0; i < PRE; i++) {
-                const uint32_t ent = p == 0 ? pre[0][i] : p == 1 ? pre[1][i] : pre[2][i];
-                if ((uint32_t)i < n) put(ent);
+                for (int i = 0; i < PRE_Y; i++) put(preY[i]);
+                i0 = PRE_Y;
+            } else {
+#pragma unroll
+                for (int i = 0; i < PRE_C; i++) put(p == 1 ? preC[0][i] : preC[1][i]);
+                i0 = PRE_C;
             }
             const uint32_t nmax = __reduce_max_sync(FULL_MASK, n);        // warp-uniform trip count
-            for (uint32_t i = PRE; i < nmax; i += 2) {                    // rest of the list, two loads in flight
-                const uint32_t e0 = i < n ? __ldg(src + i) : 0u;
-                const uint32_t e1 = i + 1 < n ? __ldg(src + i + 1) : 0u;
-                if (i < n) put(e0);
-                if (i + 1 < n) put(e1);
+            if (i0 < nmax) {                                              // rest of the list: two loads in flight, one pair ahead
+                uint32_t e0 = i0 < n ? __ldg(src + i0) : 0u, e1 = i0 + 1 < n ? __ldg(src + i0 + 1) : 0u;
+                for (uint32_t i = i0; i < nmax; i += 2) {
+                    const uint32_t n0 = i + 2 < n ? __ldg(src + i + 2) : 0u;
+                    const uint32_t n1 = i + 3 < n ? __ldg(src + i + 3) : 0u;
+                    put(e0); put(e1);
+                    e0 = n0; e1 = n1;
+                }
             }
+            *reinterpret_cast<int16_t*>(my_coef) = (int16_t)((int)(int16_t)(pmeta & 0xFFFFu) * (int)(zq[0].x >> 16));  // lossless_decode.c:94-95
             __syncwarp();
             const uint32_t m_all = warp_or(m_bits);                       // warp-uniform from here on
             const uint32_t acm = m_all >> 8, anym = m_all & 0xFFu;
@@ -307,7 +332,7 @@ cudaError_t launch_decode_fused(const EntropyJob& j, const int16_t* d_quant, voi
     const uint64_t n_tiles = (uint64_t)((nb + 31) / 32) * n_frames;
     const uint64_t want = (n_tiles + FUSED_TPB / 32 - 1) / (FUSED_TPB / 32);
     const unsigned grid = (unsigned)(want < (uint64_t)n_sm ? want : (uint64_t)n_sm);     // persistent: one CTA per SM
-    k_decode_fused<<<grid, FUSED_TPB, FUSED_SMEM, s>>>(j.d_streams + j.stream_lo, j.d_blk_info, j.d_sym,
+    k_decode_fused<<<grid, FUSED_TPB, FUSED_SMEM, s>>>(j.d_blk_info + (size_t)j.stream_lo * nb, j.d_sym,
                                                        j.d_seg_dc + j.sym_seg0, d_quant, (uint8_t*)d_out, nb, wb, W, n_frames);
     return cudaGetLastError();
 }
