@@ -56,40 +56,34 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     sd.byte_off = 0; sd.byte_len = (uint32_t)len; sd.nb = (uint32_t)num_blocks; sd.seg_base = 0;
     sd.nseg = std::max<uint32_t>(1, ((uint32_t)len + SEG_BYTES - 1) / SEG_BYTES);
     sd.block_base = 0; sd.prev_base = 0; sd.quant_id = 0; sd.ptype = P ? 1 : 0;   // P: accumulate in place
-    std::vector<TileDesc> sync_tiles, write_tiles;
-    for (uint32_t s0 = 0; s0 < sd.nseg; s0 += ENT_TPB - 1) sync_tiles.push_back({0u, s0});
-    for (uint32_t s0 = 0; s0 < sd.nseg; s0 += ENT_TPB) write_tiles.push_back({0u, s0});
-    const size_t b_sync = sync_tiles.size() * sizeof(TileDesc), b_write = write_tiles.size() * sizeof(TileDesc);
     const size_t coef_bytes = (size_t)num_blocks * 128;
     int rc;
     if ((rc = s_in.reserve(len + 64))) return rc;
-    if ((rc = s_tab.reserve(256 + 256 + b_sync + b_write))) return rc;
-    if ((rc = s_seg.reserve((size_t)sd.nseg * 20 + 96))) return rc;
+    if ((rc = s_tab.reserve(256 + 256))) return rc;
+    if ((rc = s_seg.reserve((size_t)sd.nseg * 24 + 96))) return rc;
     if ((rc = s_idx.reserve((size_t)num_blocks * 8 + (size_t)sd.nseg * SYM_STRIDE * 4 + 128))) return rc;
     if ((rc = s_mid.reserve(coef_bytes))) return rc;
     uint8_t* tab = s_tab.as<uint8_t>();
     int16_t* d_q = reinterpret_cast<int16_t*>(tab);                  // 128 int16 (table 0 used)
     StreamDesc* d_sd = reinterpret_cast<StreamDesc*>(tab + 256);
-    TileDesc* d_sync = reinterpret_cast<TileDesc*>(tab + 512);
-    TileDesc* d_write = reinterpret_cast<TileDesc*>(tab + 512 + b_sync);
     CUX(cudaMemcpyAsync(s_in.p, bitstream, len, cudaMemcpyHostToDevice, s));
     CUX(cudaMemsetAsync(s_in.as<uint8_t>() + len, 0, 64, s));
     CUX(cudaMemcpyAsync(d_q, quant, 128, cudaMemcpyHostToDevice, s));
     CUX(cudaMemcpyAsync(d_sd, &sd, sizeof(sd), cudaMemcpyHostToDevice, s));
-    CUX(cudaMemcpyAsync(d_sync, sync_tiles.data(), b_sync, cudaMemcpyHostToDevice, s));
-    CUX(cudaMemcpyAsync(d_write, write_tiles.data(), b_write, cudaMemcpyHostToDevice, s));
     if (P) CUX(cudaMemcpyAsync(s_mid.p, DCACq, coef_bytes, cudaMemcpyHostToDevice, s));   // in/out state
     EntropyJob j;
     j.d_payload = s_in.as<uint8_t>();
-    j.d_streams = d_sd; j.d_sync_tiles = d_sync; j.d_write_tiles = d_write;
+    j.d_streams = d_sd;
     j.stream_lo = 0; j.n_streams = 1;
-    j.n_sync_tiles = (uint32_t)sync_tiles.size(); j.n_write_tiles = (uint32_t)write_tiles.size();
+    j.seg_lo = 0; j.seg_hi = sd.nseg;
     uint32_t* seg = s_seg.as<uint32_t>();
+    CUX(cudaMemsetAsync(seg + 5 * (size_t)sd.nseg, 0, (size_t)sd.nseg * 4, s));   // every segment belongs to stream 0
+    j.d_seg_stream = seg + 5 * (size_t)sd.nseg;
     j.d_seg_entry = seg; j.d_seg_exit = seg + sd.nseg; j.d_seg_cnt = seg + 2 * (size_t)sd.nseg;
     j.d_seg_first = seg + 3 * (size_t)sd.nseg;
     j.d_seg_dc = seg + 4 * (size_t)sd.nseg;
-    j.d_stream_blocks = seg + 5 * (size_t)sd.nseg;
-    j.d_fixups = reinterpret_cast<unsigned long long*>(seg + ((5 * (size_t)sd.nseg + 3) & ~(size_t)1));
+    j.d_stream_blocks = seg + 6 * (size_t)sd.nseg;
+    j.d_fixups = reinterpret_cast<unsigned long long*>(seg + ((6 * (size_t)sd.nseg + 3) & ~(size_t)1));
     j.d_blk_info = s_idx.as<uint2>();
     j.d_sym = s_idx.as<uint32_t>() + ((2 * (size_t)num_blocks + 7) & ~(size_t)7);
     j.sym_seg0 = 0;

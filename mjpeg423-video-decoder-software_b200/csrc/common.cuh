@@ -45,12 +45,6 @@ struct StreamDesc {
     uint16_t ptype;        // 0 = I frame (zero-fill, DC differential), 1 = P frame (accumulate)
 };
 
-// A CTA-sized run of consecutive segments of one stream.
-struct TileDesc {
-    uint32_t stream;       // index into the StreamDesc array
-    uint32_t seg0;         // first segment (within the stream) owned by this tile
-};
-
 // ------------------------------------------------------------------------------------------------
 // Symbol stepper shared by every segment-parallel pass (speculative parse, merge, chain re-parse,
 // block index) so that they all follow ONE trajectory function.  The passes run a single flat loop,
@@ -68,9 +62,10 @@ struct TileDesc {
 // (w0 = current, w1 = next).  Positions are counted from the ALIGNED word that holds the stream's first
 // byte ("f" positions = stream bit position + bias, bias = 8 * (address & 3)), so the offset into w0 is
 // simply fpos & 31: the next 32 stream bits are ONE funnel shift (which takes its amount mod 32) and a
-// word crossing is bit 5 of fpos flipping.  The look-ahead word is fetched a whole word (3-4 symbols)
-// before it is needed.  The payload buffer is padded: reads up to 16 bytes past any stream end are in
-// bounds.
+// word crossing is bit 5 of fpos flipping.  A third word w2 is in flight behind them: the funnel shift reads
+// w1 in EVERY step, so a word loaded straight into w1 would be waited for one step later; loaded into w2 it
+// is not touched until the next crossing (3-4 symbols), which hides an L2 round trip.  The payload buffer
+// is padded: reads up to 16 bytes past any stream end are in bounds.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t stream_bias(const uint8_t* base) {
     return (uint32_t)(reinterpret_cast<uintptr_t>(base) & 3u) * 8u;
@@ -78,7 +73,7 @@ __device__ __forceinline__ uint32_t stream_bias(const uint8_t* base) {
 
 struct Parser {
     const uint32_t* wp;    // next aligned word to fetch
-    uint32_t w0, w1;       // current and look-ahead word, MSB first
+    uint32_t w0, w1, w2;   // current word, look-ahead word, word in flight; MSB first
     uint32_t fpos;         // f position of the next symbol
     uint32_t flim;         // the current block is ended at or after this f position
     uint32_t idx;          // zig-zag index of the next AC coefficient
@@ -90,7 +85,8 @@ struct Parser {
         const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)3) + (fbits >> 5);
         w0 = __byte_perm(__ldg(w), 0, 0x0123);
         w1 = __byte_perm(__ldg(w + 1), 0, 0x0123);
-        wp = w + 2;
+        w2 = __ldg(w + 2);                               // kept raw: byte-swapped when it moves into w1
+        wp = w + 3;
         fpos = fbits;
         flim = min(fbits + RUNAWAY_BITS, ftotal);
         idx = 1;
@@ -103,7 +99,7 @@ struct Parser {
     // and the pass ignores what it returns.
     __device__ __forceinline__ void park() { rmask = 0u; w0 = 0u; w1 = 0u; }
     __device__ __forceinline__ void init_parked() {
-        wp = nullptr; w0 = w1 = 0u; fpos = 0u; flim = 0u; idx = 1u; nh = (uint32_t)-4; rmask = 0u;
+        wp = nullptr; w0 = w1 = w2 = 0u; fpos = 0u; flim = 0u; idx = 1u; nh = (uint32_t)-4; rmask = 0u;
     }
 
     // What the last step() consumed.
@@ -132,9 +128,10 @@ struct Parser {
         } else {
             sym.e = 0;
         }
-        if ((fpos ^ fnew) & rmask) {                                    // crossed into w1: fetch the word after it
+        if ((fpos ^ fnew) & rmask) {                                    // crossed into w1: fetch the word after w2
             w0 = w1;
-            w1 = __byte_perm(__ldg(wp), 0, 0x0123);
+            w1 = __byte_perm(w2, 0, 0x0123);
+            w2 = __ldg(wp);
             wp++;
         }
         const bool szd = size != 0u || dc;

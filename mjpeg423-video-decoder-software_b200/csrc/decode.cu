@@ -159,80 +159,113 @@ k_decode_fused(const uint2* __restrict__ blk_info,
     // fetched one tile AHEAD, so that a tile starts with its list addresses known and only one load latency
     // (the lists) is exposed instead of two dependent ones.
     const uint32_t tile_step = gridDim.x * warps_per_cta;
+    const uint32_t lane = (uint32_t)t & 31u;
+    uint8_t* warp_coef = s_coef + ((uint32_t)t & ~31u) * 16u;            // slot of lane 0 of this warp
     auto load_info = [&](uint32_t tile_, uint2 (&inf)[3]) {
         const uint32_t f_ = tile_ / tiles_per_frame;
-        const uint32_t b_ = (tile_ - f_ * tiles_per_frame) * 32u + (uint32_t)(t & 31);
+        const uint32_t b_ = (tile_ - f_ * tiles_per_frame) * 32u + lane;
 #pragma unroll
         for (int p = 0; p < 3; p++)
             inf[p] = (tile_ < n_tiles && b_ < nb) ? __ldg(blk_info + (size_t)(f_ * 3u + p) * nb + b_) : make_uint2(BLK_NO_SEG, 0u);
     };
+    // The lists of consecutive blocks of a segment are consecutive in memory, so the 32 lists of a tile form
+    // one contiguous run of entries (a new run starts where the tile crosses into the next bitstream segment).
+    // first_run(): entry range [r0, r1) of the run that starts at lane 0; `rest` = first lanes of the other runs.
+    auto first_run = [&](uint32_t x, uint32_t xe, uint32_t& r0, uint32_t& r1, uint32_t& rest) {
+        const uint32_t prev_e = __shfl_up_sync(FULL_MASK, xe, 1);
+        rest = __ballot_sync(FULL_MASK, lane != 0u && x != prev_e);
+        r0 = __shfl_sync(FULL_MASK, x, 0);
+        r1 = __shfl_sync(FULL_MASK, xe, rest ? __ffs(rest) - 2 : 31);
+    };
+    // The head of every plane's first run (4 x 32 luminance entries, 32 of each chrominance plane: most of a
+    // tile at the usual rates) is fetched one tile ahead as well, behind the IDCTs of the current tile.
+    constexpr int PRE_Y = 4;
     uint2 ninfo[3];
+    uint32_t npreY[PRE_Y], npreC[2];
+    auto prefetch_lists = [&]() {
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            uint32_t r0, r1, rest;
+            first_run(ninfo[p].x, ninfo[p].x + (ninfo[p].y >> 16), r0, r1, rest);
+            if (p == 0) {
+#pragma unroll
+                for (int i = 0; i < PRE_Y; i++) npreY[i] = lane + 32u * i < r1 - r0 ? __ldg(sym + (r0 + lane + 32u * i)) : 0u;
+            } else {
+                npreC[p - 1] = lane < r1 - r0 ? __ldg(sym + (r0 + lane)) : 0u;
+            }
+        }
+    };
     uint32_t tile = blockIdx.x * warps_per_cta + (uint32_t)(t >> 5);
     load_info(tile, ninfo);
+    prefetch_lists();
 
     for (; tile < n_tiles; tile += tile_step) {
         const uint32_t f = tile / tiles_per_frame;
-        const uint32_t b = (tile - f * tiles_per_frame) * 32u + (uint32_t)(t & 31);
+        const uint32_t b = (tile - f * tiles_per_frame) * 32u + lane;
         const bool live = b < nb;
         uint8_t* dst = out + ((size_t)f * nb * 64 + ((size_t)(b / wb) * 8 * W + (size_t)(b % wb) * 8)) * 4;
 
-        // The first PRE list entries of each plane (luminance blocks hold most of the coefficients) are fetched up
-        // front: independent loads in flight per lane instead of a dependent load per coefficient.  Entries past
-        // the end of a list read as 0 = "coefficient 0, amplitude 0": scattering one only clears the DC slot, which
-        // is written afterwards.
-        constexpr int PRE_Y = 8, PRE_C = 2;
-        uint32_t meta[3], preY[PRE_Y], preC[2][PRE_C];
-        const uint32_t* lst[3];
+        uint32_t meta[3], lx[3], lxe[3], preY[PRE_Y], preC[2];
 #pragma unroll
-        for (int p = 0; p < 3; p++) lst[p] = sym + ninfo[p].x;
+        for (int p = 0; p < 3; p++) { lx[p] = ninfo[p].x; lxe[p] = ninfo[p].x + (ninfo[p].y >> 16); meta[p] = absolute_dc(ninfo[p], seg_dc); }
 #pragma unroll
-        for (int i = 0; i < PRE_Y; i++) preY[i] = (uint32_t)i < (ninfo[0].y >> 16) ? __ldg(lst[0] + i) : 0u;
-#pragma unroll
-        for (int p = 1; p < 3; p++)
-#pragma unroll
-            for (int i = 0; i < PRE_C; i++) preC[p - 1][i] = (uint32_t)i < (ninfo[p].y >> 16) ? __ldg(lst[p] + i) : 0u;
-#pragma unroll
-        for (int p = 0; p < 3; p++) meta[p] = absolute_dc(ninfo[p], seg_dc);
+        for (int i = 0; i < PRE_Y; i++) preY[i] = npreY[i];
+        preC[0] = npreC[0]; preC[1] = npreC[1];
         load_info(tile + tile_step, ninfo);
 
         bool cb_flat = false;                                            // warp-uniform: every Cb block of the tile is DC-only
 #pragma unroll 1
         for (int p = 0; p < 3; p++) {
-            // ---- scatter this plane's block into the (zeroed) transposed coefficient slot -----------------
+            // ---- scatter this plane's blocks into the (zeroed) transposed coefficient slots -----------------
 #pragma unroll
             for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(my_coef + c * (FUSED_TPB * 16)) = make_uint4(0, 0, 0, 0);
             // (p is a loop variable: select the pre-fetched registers without dynamic indexing)
             const uint32_t pmeta = p == 0 ? meta[0] : p == 1 ? meta[1] : meta[2];
-            const uint32_t* src = p == 0 ? lst[0] : p == 1 ? lst[1] : lst[2];
+            const uint32_t x = p == 0 ? lx[0] : p == 1 ? lx[1] : lx[2];
+            const uint32_t xe = p == 0 ? lxe[0] : p == 1 ? lxe[1] : lxe[2];
             const uint2* zq = s_zq + (p ? 64 : 0);
-            const uint32_t n = pmeta >> 16;
+            *reinterpret_cast<int16_t*>(my_coef) = (int16_t)((int)(int16_t)(pmeta & 0xFFFFu) * (int)(zq[0].x >> 16));  // lossless_decode.c:94-95
+            if (p == 1) prefetch_lists();                                 // next tile's lists (its index arrived during plane 0)
+            __syncwarp();
+            // The WARP reads each run with coalesced loads, and whichever lane holds an entry dequantises it and
+            // stores it into the slot of the lane that owns the block (entry bits 6..10, written by
+            // k_entropy_index): no lane waits for the longest list of the tile, no load depends on another.
             uint32_t m_bits = 1u;                                         // column 0 always holds the DC coefficient
             auto put = [&](uint32_t ent) {                                // dequantise + scatter one entry (:125)
                 const uint2 z = zq[ent & 63u];
-                *reinterpret_cast<int16_t*>(my_coef + (z.x & 0xFFFFu)) = (int16_t)(((int)ent >> 16) * (int)(z.x >> 16));
+                *reinterpret_cast<int16_t*>(warp_coef + ((ent >> 2) & 0x1F0u) + (z.x & 0xFFFFu)) =
+                    (int16_t)(((int)ent >> 16) * (int)(z.x >> 16));
                 m_bits |= z.y;
             };
-            uint32_t i0;                                                  // entries scattered from the registers
-            if (p == 0) {
+            uint32_t r0, r1, rest, a;
+            first_run(x, xe, r0, r1, rest);
+            if (p == 0) {                                                 // head of the first run: already in registers
 #pragma unroll
-                for (int i = 0; i < PRE_Y; i++) put(preY[i]);
-                i0 = PRE_Y;
+                for (int i = 0; i < PRE_Y; i++) if (lane + 32u * i < r1 - r0) put(preY[i]);
+                a = min(r0 + 32u * PRE_Y, r1);
             } else {
-#pragma unroll
-                for (int i = 0; i < PRE_C; i++) put(p == 1 ? preC[0][i] : preC[1][i]);
-                i0 = PRE_C;
+                if (lane < r1 - r0) put(p == 1 ? preC[0] : preC[1]);
+                a = min(r0 + 32u, r1);
             }
-            const uint32_t nmax = __reduce_max_sync(FULL_MASK, n);        // warp-uniform trip count
-            if (i0 < nmax) {                                              // rest of the list: two loads in flight, one pair ahead
-                uint32_t e0 = i0 < n ? __ldg(src + i0) : 0u, e1 = i0 + 1 < n ? __ldg(src + i0 + 1) : 0u;
-                for (uint32_t i = i0; i < nmax; i += 2) {
-                    const uint32_t n0 = i + 2 < n ? __ldg(src + i + 2) : 0u;
-                    const uint32_t n1 = i + 3 < n ? __ldg(src + i + 3) : 0u;
-                    put(e0); put(e1);
-                    e0 = n0; e1 = n1;
+            for (;;) {                                                    // warp-uniform: rest of the run, then the other runs
+                for (; a < r1; a += 128u) {                               // four coalesced loads in flight
+                    const uint32_t i0 = a + lane, i1 = i0 + 32u, i2 = i0 + 64u, i3 = i0 + 96u;
+                    const uint32_t e0 = i0 < r1 ? __ldg(sym + i0) : 0u;
+                    const uint32_t e1 = i1 < r1 ? __ldg(sym + i1) : 0u;
+                    const uint32_t e2 = i2 < r1 ? __ldg(sym + i2) : 0u;
+                    const uint32_t e3 = i3 < r1 ? __ldg(sym + i3) : 0u;
+                    if (i0 < r1) put(e0);
+                    if (i1 < r1) put(e1);
+                    if (i2 < r1) put(e2);
+                    if (i3 < r1) put(e3);
                 }
+                if (!rest) break;
+                const int s0 = __ffs(rest) - 1;
+                rest &= rest - 1u;
+                r0 = __shfl_sync(FULL_MASK, x, s0);
+                r1 = __shfl_sync(FULL_MASK, xe, rest ? __ffs(rest) - 2 : 31);
+                a = r0;
             }
-            *reinterpret_cast<int16_t*>(my_coef) = (int16_t)((int)(int16_t)(pmeta & 0xFFFFu) * (int)(zq[0].x >> 16));  // lossless_decode.c:94-95
             __syncwarp();
             const uint32_t m_all = warp_or(m_bits);                       // warp-uniform from here on
             const uint32_t acm = m_all >> 8, anym = m_all & 0xFFu;

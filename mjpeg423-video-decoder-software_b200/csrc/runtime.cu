@@ -81,12 +81,10 @@ int build_plan(const MpgIndex& idx, uint32_t first, uint32_t n, Plan& plan) {
     plan.payload_off = plan.frames.front().off;
     plan.payload_len = plan.frames.back().off + plan.frames.back().size - plan.payload_off;
     plan.streams.reserve((size_t)n * 3);
-    plan.f_sync0.resize(n + 1); plan.f_write0.resize(n + 1); plan.f_seg0.resize(n + 1);
+    plan.f_seg0.resize(n + 1);
     uint32_t seg_base = 0;
     for (uint32_t f = 0; f < n; f++) {
         const FrameRec& r = plan.frames[f];
-        plan.f_sync0[f] = (uint32_t)plan.sync_tiles.size();
-        plan.f_write0[f] = (uint32_t)plan.write_tiles.size();
         plan.f_seg0[f] = seg_base;
         const uint32_t lens[3] = {r.ysize, r.cbsize, r.crsize};
         uint64_t so = r.off + 16 - plan.payload_off;
@@ -99,16 +97,11 @@ int build_plan(const MpgIndex& idx, uint32_t first, uint32_t n, Plan& plan) {
             sd.block_base = (f * 3 + p) * plan.nb;
             sd.prev_base = r.type ? sd.block_base - 3 * plan.nb : sd.block_base;   // frame 0 is an I frame
             sd.quant_id = p ? 1 : 0; sd.ptype = (uint16_t)r.type;
-            const uint32_t sidx = (uint32_t)plan.streams.size();
-            for (uint32_t s0 = 0; s0 < sd.nseg; s0 += ENT_TPB - 1) plan.sync_tiles.push_back({sidx, s0});
-            for (uint32_t s0 = 0; s0 < sd.nseg; s0 += ENT_TPB) plan.write_tiles.push_back({sidx, s0});
             plan.streams.push_back(sd);
             seg_base += sd.nseg; so += lens[p];
             plan.stream_bytes += lens[p];
         }
     }
-    plan.f_sync0[n] = (uint32_t)plan.sync_tiles.size();
-    plan.f_write0[n] = (uint32_t)plan.write_tiles.size();
     plan.f_seg0[n] = seg_base;
     return MJPEG423_OK;
 }
@@ -263,8 +256,8 @@ extern "C" int mjpeg423_b200_probe(const uint8_t* mpg, size_t len, mjpeg423_b200
 namespace {
 
 struct Tables {           // device addresses inside ctx->tables / ctx->segs
-    StreamDesc* streams; TileDesc* sync_tiles; TileDesc* write_tiles;
-    uint32_t *seg_entry, *seg_exit, *seg_cnt, *seg_first, *seg_dc, *stream_blocks;
+    StreamDesc* streams;
+    uint32_t *seg_stream, *seg_entry, *seg_exit, *seg_cnt, *seg_first, *seg_dc, *stream_blocks;
     unsigned long long* fixups;
 };
 
@@ -272,12 +265,7 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 Tables tables_of(mjpeg423_b200_ctx* c, const Plan& plan) {
     Tables t;
-    const size_t b_streams = align256(plan.streams.size() * sizeof(StreamDesc));
-    const size_t b_sync = align256(plan.sync_tiles.size() * sizeof(TileDesc));
-    uint8_t* base = c->tables.as<uint8_t>();
-    t.streams = reinterpret_cast<StreamDesc*>(base);
-    t.sync_tiles = reinterpret_cast<TileDesc*>(base + b_streams);
-    t.write_tiles = reinterpret_cast<TileDesc*>(base + b_streams + b_sync);
+    t.streams = c->tables.as<StreamDesc>();
     const size_t nseg = plan.f_seg0.empty() ? 0 : plan.f_seg0.back();
     const size_t b_seg = align256(nseg * 4), b_sb = align256(plan.streams.size() * 4);
     uint8_t* sb = c->segs.as<uint8_t>();
@@ -286,25 +274,22 @@ Tables tables_of(mjpeg423_b200_ctx* c, const Plan& plan) {
     t.seg_cnt = reinterpret_cast<uint32_t*>(sb + 2 * b_seg);
     t.seg_first = reinterpret_cast<uint32_t*>(sb + 3 * b_seg);
     t.seg_dc = reinterpret_cast<uint32_t*>(sb + 4 * b_seg);
-    t.stream_blocks = reinterpret_cast<uint32_t*>(sb + 5 * b_seg);
-    t.fixups = reinterpret_cast<unsigned long long*>(sb + 5 * b_seg + b_sb);
+    t.seg_stream = reinterpret_cast<uint32_t*>(sb + 5 * b_seg);
+    t.stream_blocks = reinterpret_cast<uint32_t*>(sb + 6 * b_seg);
+    t.fixups = reinterpret_cast<unsigned long long*>(sb + 6 * b_seg + b_sb);
     return t;
 }
 
 // Lays the plan's tables out in ctx->tables (uploaded) and ctx->segs (device scratch).
 int upload_tables(mjpeg423_b200_ctx* c, const Plan& plan, Tables& t, cudaStream_t s) {
-    const size_t b_streams = align256(plan.streams.size() * sizeof(StreamDesc));
-    const size_t b_sync = align256(plan.sync_tiles.size() * sizeof(TileDesc));
-    const size_t b_write = align256(plan.write_tiles.size() * sizeof(TileDesc));
-    int rc = c->tables.reserve(b_streams + b_sync + b_write + 256);
+    int rc = c->tables.reserve(plan.streams.size() * sizeof(StreamDesc) + 256);
     if (rc) return rc;
     const size_t nseg = plan.f_seg0.empty() ? 0 : plan.f_seg0.back();
-    rc = c->segs.reserve(5 * align256(nseg * 4) + align256(plan.streams.size() * 4) + 256);   // ... + 2 x u64 counters
+    rc = c->segs.reserve(6 * align256(nseg * 4) + align256(plan.streams.size() * 4) + 256);   // ... + 2 x u64 counters
     if (rc) return rc;
     t = tables_of(c, plan);
     CU(cudaMemcpyAsync(t.streams, plan.streams.data(), plan.streams.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(t.sync_tiles, plan.sync_tiles.data(), plan.sync_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(t.write_tiles, plan.write_tiles.data(), plan.write_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
+    CU(launch_seg_stream(t.streams, (uint32_t)plan.streams.size(), t.seg_stream, s));
     c->chunk_K = 0;      // chunk table must be rebuilt for this plan
     return MJPEG423_OK;
 }
@@ -365,11 +350,9 @@ EntropyJob make_job(const Plan& plan, const Tables& t, const uint8_t* d_payload_
     EntropyJob j;
     j.d_payload = d_payload_origin;
     j.d_streams = t.streams;
-    j.d_sync_tiles = t.sync_tiles + plan.f_sync0[f0];
-    j.d_write_tiles = t.write_tiles + plan.f_write0[f0];
+    j.d_seg_stream = t.seg_stream;
+    j.seg_lo = plan.f_seg0[f0]; j.seg_hi = plan.f_seg0[f1];
     j.stream_lo = f0 * 3; j.n_streams = (f1 - f0) * 3;
-    j.n_sync_tiles = plan.f_sync0[f1] - plan.f_sync0[f0];
-    j.n_write_tiles = plan.f_write0[f1] - plan.f_write0[f0];
     j.d_seg_entry = t.seg_entry; j.d_seg_exit = t.seg_exit; j.d_seg_cnt = t.seg_cnt; j.d_seg_first = t.seg_first;
     j.d_seg_dc = t.seg_dc;
     j.d_stream_blocks = t.stream_blocks; j.d_fixups = t.fixups;

@@ -13,15 +13,14 @@
 namespace mj {
 
 // Device view of the entropy stage for one launch (one chunk of frames).  All table pointers are
-// already offset so that the indices stored in StreamDesc / TileDesc (which are relative to the whole
+// already offset so that the indices stored in StreamDesc (which are relative to the whole
 // plan) address the right element.
 struct EntropyJob {
     const uint8_t* d_payload = nullptr;          // address of plan.payload_off (may lie before the chunk's buffer)
     const StreamDesc* d_streams = nullptr;       // plan-wide table
-    const TileDesc* d_sync_tiles = nullptr;      // first sync tile of the chunk
-    const TileDesc* d_write_tiles = nullptr;     // first write tile of the chunk
+    const uint32_t* d_seg_stream = nullptr;      // plan-wide: global segment -> stream
+    uint32_t seg_lo = 0, seg_hi = 0;             // global segments of the chunk
     uint32_t stream_lo = 0, n_streams = 0;       // streams of the chunk (chain kernel: one CTA each)
-    uint32_t n_sync_tiles = 0, n_write_tiles = 0;
     uint32_t *d_seg_entry = nullptr, *d_seg_exit = nullptr, *d_seg_cnt = nullptr, *d_seg_first = nullptr; // plan-wide
     uint32_t* d_seg_dc = nullptr;                // plan-wide: DC total, then DC predictor, of every segment
     uint32_t* d_stream_blocks = nullptr;         // plan-wide, per stream
@@ -31,6 +30,7 @@ struct EntropyJob {
     uint32_t sym_seg0 = 0;
 };
 
+cudaError_t launch_seg_stream(const StreamDesc* d_streams, uint32_t n_streams, uint32_t* d_seg_stream, cudaStream_t s);
 cudaError_t launch_entropy_sync(const EntropyJob& j, cudaStream_t s);
 cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s);
 cudaError_t launch_entropy_index(const EntropyJob& j, cudaStream_t s);
@@ -63,8 +63,7 @@ struct Plan {
     uint64_t payload_off = 0, payload_len = 0;   // byte range of the file covered by the frames
     std::vector<FrameRec> frames;
     std::vector<StreamDesc> streams;             // 3 per frame: Y, Cb, Cr
-    std::vector<TileDesc> sync_tiles, write_tiles;
-    std::vector<uint32_t> f_sync0, f_write0, f_seg0;   // n+1 prefix tables per frame
+    std::vector<uint32_t> f_seg0;                // n+1: first global segment of every frame
     uint64_t stream_bytes = 0;                   // sum of plane stream lengths
     uint32_t n_pframes = 0;
 };
