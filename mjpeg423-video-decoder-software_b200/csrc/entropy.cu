@@ -308,15 +308,21 @@ k_entropy_chain(const uint8_t* __restrict__ payload, const StreamDesc* __restric
     volatile uint32_t* v_cnt = seg_cnt + sd.seg_base;
     const int t = threadIdx.x;
 
-    // 1. make the chain exact: entry[0] = 0, entry[i] = exit[i-1].
+    // 1. make the chain exact: entry[0] = 0, entry[i] = exit[i-1].  Every thread owns a CONTIGUOUS range of
+    // segments and ripples through it in order: a re-parsed segment's new exit is handed to the next segment
+    // at once, so a stream that does not self-synchronise (e.g. blocks that all end on coefficient 63: the
+    // zig-zag index then never re-aligns quickly) costs one parse per segment plus a few rounds across range
+    // boundaries -- not one round per segment.
     uint32_t nfix = 0;
-    for (uint32_t sweep = 0; sweep <= sd.nseg + 1; sweep++) {   // converges in <= nseg sweeps; bound it anyway
+    const uint32_t per = (sd.nseg + CHAIN_TPB - 1) / CHAIN_TPB;
+    const uint32_t i_lo = min(sd.nseg, (uint32_t)t * per), i_hi = min(sd.nseg, i_lo + per);
+    for (uint32_t round = 0; round <= CHAIN_TPB + 1; round++) {   // converges in <= CHAIN_TPB rounds; bound it anyway
         int changed = 0;
-        for (uint32_t i = t; i < sd.nseg; i += CHAIN_TPB) {
-            uint32_t E = i ? v_exit[i - 1] : 0u;
+        for (uint32_t i = i_lo; i < i_hi; i++) {
+            const uint32_t E = i ? v_exit[i - 1] : 0u;
             if (v_entry[i] != E) {
                 uint32_t cnt;
-                uint32_t x = parse_segment(base, E + bias, (i + 1) * SEG_BITS + bias, ftotal, cnt) - bias;
+                const uint32_t x = parse_segment(base, E + bias, (i + 1) * SEG_BITS + bias, ftotal, cnt) - bias;
                 v_entry[i] = E;
                 v_exit[i] = x;
                 v_cnt[i] = cnt;
@@ -324,6 +330,7 @@ k_entropy_chain(const uint8_t* __restrict__ payload, const StreamDesc* __restric
                 nfix++;
             }
         }
+        __threadfence_block();
         if (!__syncthreads_or(changed)) break;
     }
     if (nfix) atomicAdd(fixups, (unsigned long long)nfix);
