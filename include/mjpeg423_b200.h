@@ -184,6 +184,23 @@ int   mjpeg423_b200_device_count(void);
 int   mjpeg423_b200_hash_frames(mjpeg423_b200_ctx* ctx, const void* d_frames, uint64_t frame_bytes, uint32_t n,
                                 uint64_t* hashes);
 
+/* ---- 4. encoder: LIB/encoder/mjpeg423_encoder.h ---------------------------------- */
+/* The frame loop of mjpeg423_encode(), LIB/encoder/mjpeg423_encoder.c:97-225, on in-memory frames: n frames of
+ * w_size x h_size rgb_pixel_t (BGRA, top-down raster -- what decode_bmp() hands the reference, alpha ignored),
+ * in host memory or (frames_on_device != 0) on the context's device, are colour-converted, transformed,
+ * quantised with the context's tables (mjpeg423_b200_set_quant), coded as I or P frames by the reference's rule
+ * (I when first frame, I not larger than P, or max_I_interval frames after the last I frame) and written as a
+ * complete .mpg into the HOST buffer `mpg` of `cap` bytes; *mpg_len receives its length.  The
+ * file equals the reference encoder's byte for byte, except its last 512 bytes (uninitialised stack in the
+ * reference, zeros here).  The BMP reader of the reference (libnsbmp) is file I/O and stays with the caller.
+ * flags: MJPEG423_ENC_FIX_TAIL writes the last partial byte of every plane stream; by default it is 0 like the
+ * reference's (output_rest, LIB/encoder/lossless_encode.c:80-83). */
+#define MJPEG423_ENC_FIX_TAIL 1u
+size_t mjpeg423_b200_encode_bound(uint32_t n, uint32_t w_size, uint32_t h_size);   /* a sufficient `cap` */
+int mjpeg423_b200_encode_frames(mjpeg423_b200_ctx* ctx, const void* frames, int frames_on_device, uint32_t n,
+                                uint32_t w_size, uint32_t h_size, uint32_t max_I_interval, uint32_t flags,
+                                uint8_t* mpg, size_t cap, size_t* mpg_len);
+
 #ifdef __cplusplus
 }
 #endif

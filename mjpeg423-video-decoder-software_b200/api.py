@@ -50,6 +50,7 @@ EXPORTS = [
     "mjpeg423_b200_host_alloc", "mjpeg423_b200_host_free", "mjpeg423_b200_device_alloc",
     "mjpeg423_b200_device_free", "mjpeg423_b200_memcpy_d2h", "mjpeg423_b200_memcpy_h2d", "mjpeg423_b200_sync",
     "mjpeg423_b200_device_count", "mjpeg423_b200_hash_frames",
+    "mjpeg423_b200_encode_bound", "mjpeg423_b200_encode_frames",
 ]
 
 
@@ -136,6 +137,8 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "mjpeg423_b200_sync": (i32, [p]),
         "mjpeg423_b200_device_count": (i32, []),
         "mjpeg423_b200_hash_frames": (i32, [p, p, u64, u32, p]),
+        "mjpeg423_b200_encode_bound": (sz, [u32, u32, u32]),
+        "mjpeg423_b200_encode_frames": (i32, [p, p, i32, u32, u32, u32, u32, u32, p, sz, C.POINTER(sz)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -315,6 +318,26 @@ class Decoder:
         rc = self.lib.mjpeg423_b200_decode_frames(self.h, a.ctypes.data, a.size, first, n, arr.ctypes.data, 0)
         _check(self.lib, rc, "decode_frames")
         return arr.reshape(-1)[:nbytes].reshape(n, info.h_size, info.w_size, 4)
+
+    # -- encoder: frames -> .mpg, the loop of LIB/encoder/mjpeg423_encoder.c:97-225 ----------
+    def encode_frames(self, frames, max_I_interval: int = 1, fix_tail: bool = False, d_frames: int = 0,
+                      shape: tuple | None = None) -> np.ndarray:
+        """frames: (n, H, W, 4) uint8 BGRA on the host -- or d_frames = device pointer with shape = (n, H, W).
+        Returns the .mpg bytes (byte-identical to the reference encoder up to its last 512 bytes)."""
+        if d_frames:
+            n, H, W = shape
+            src, on_dev = d_frames, 1
+        else:
+            fr = np.ascontiguousarray(frames, dtype=np.uint8)
+            n, H, W, _ = fr.shape
+            src, on_dev = fr.ctypes.data, 0
+        cap = self.lib.mjpeg423_b200_encode_bound(n, W, H)
+        out = np.empty(cap, dtype=np.uint8)
+        ln = C.c_size_t(0)
+        rc = self.lib.mjpeg423_b200_encode_frames(self.h, src, on_dev, n, W, H, max_I_interval, 1 if fix_tail else 0,
+                                                  out.ctypes.data, out.size, C.byref(ln))
+        _check(self.lib, rc, "encode_frames")
+        return out[:ln.value]
 
     def decode_frames_to_device(self, mpg, d_out: int, first: int = 0, n: int | None = None) -> None:
         a = _bytes_arr(mpg)

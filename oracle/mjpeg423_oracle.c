@@ -180,3 +180,141 @@ void orc_ycbcr_to_rgb(int h, int w, uint32_t w_size, const uint8_t* Y, const uin
         }
     }
 }
+
+/* ==== encoder restatement ==================================================
+ * LIB/encoder/{rgb_to_ycbcr,fdct,quantize,lossless_encode}.c.  Pinned against the reference's own
+ * functions in oracle/_ref (tests/test_oracle.py::test_encoder_*).  Floating point: the reference
+ * evaluates the colour equations in double, left to right, and truncates to uint8_t; this file must be
+ * compiled without FMA contraction (oracle/Makefile passes -ffp-contract=off). */
+
+/* LIB/encoder/rgb_to_ycbcr.c:58-70.  rgb = BGRA raster (rgb_pixel_t, mjpeg423_types.h:56-61). */
+void orc_rgb_to_ycbcr(int h, int w, uint32_t w_size, const uint8_t* rgb, uint8_t* Y, uint8_t* Cb, uint8_t* Cr) {
+    for (int y = 0; y < 8; y++) {
+        const uint8_t* px = rgb + ((size_t)(y + h) * w_size + (size_t)w) * 4;
+        for (int x = 0; x < 8; x++, px += 4) {
+            const int B = px[0], G = px[1], R = px[2];
+            const double yy = 0.299 * R + 0.587 * G + 0.114 * B;
+            const double cb = -0.168736 * R - 0.331264 * G + 0.5 * B + 128;
+            const double cr = 0.5 * R - 0.418688 * G - 0.081312 * B + 128;
+            Y[y * 8 + x] = (uint8_t)yy;
+            Cb[y * 8 + x] = (uint8_t)cb;
+            Cr[y * 8 + x] = (uint8_t)cr;
+        }
+    }
+}
+
+/* 8-point forward LL&M stage shared by both passes of LIB/encoder/fdct.c:33-161.  `in` are the 8 inputs;
+ * out[0]/out[4] receive the two plain sums (scaled by the caller), out[1..3,5..7] the rotated terms
+ * BEFORE descaling. */
+static inline void fllm8(const int32_t in[8], int32_t sum[2], int32_t rot[8]) {
+    const int32_t t0 = in[0] + in[7], t7 = in[0] - in[7], t1 = in[1] + in[6], t6 = in[1] - in[6];
+    const int32_t t2 = in[2] + in[5], t5 = in[2] - in[5], t3 = in[3] + in[4], t4 = in[3] - in[4];
+    const int32_t t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
+    sum[0] = t10 + t11;
+    sum[1] = t10 - t11;
+    int32_t z1 = (t12 + t13) * 4433;
+    rot[2] = z1 + t13 * 6270;
+    rot[6] = z1 + t12 * -15137;
+    z1 = t4 + t7;
+    int32_t z2 = t5 + t6, z3 = t4 + t6, z4 = t5 + t7;
+    const int32_t z5 = (z3 + z4) * 9633;
+    const int32_t a4 = t4 * 2446, a5 = t5 * 16819, a6 = t6 * 25172, a7 = t7 * 12299;
+    z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;
+    z3 += z5; z4 += z5;
+    rot[7] = a4 + z1 + z3;
+    rot[5] = a5 + z2 + z4;
+    rot[3] = a6 + z2 + z3;
+    rot[1] = a7 + z1 + z4;
+}
+static inline int32_t fdescale(int32_t x, int n) { return (int32_t)(((uint32_t)x + (1u << (n - 1)))) >> n; }
+
+/* LIB/encoder/fdct.c:17-161: rows (results scaled up by 2^PASS1_BITS, stored as int16), then columns. */
+void orc_fdct(const uint8_t* block, int16_t* DCAC) {
+    for (int r = 0; r < 8; r++) {
+        int32_t in[8], sum[2], rot[8];
+        for (int k = 0; k < 8; k++) in[k] = block[r * 8 + k];
+        fllm8(in, sum, rot);
+        DCAC[r * 8 + 0] = (int16_t)(sum[0] << 2);
+        DCAC[r * 8 + 4] = (int16_t)(sum[1] << 2);
+        for (int k = 1; k < 8; k++) if (k != 4) DCAC[r * 8 + k] = (int16_t)fdescale(rot[k], 11);
+    }
+    for (int c = 0; c < 8; c++) {
+        int32_t in[8], sum[2], rot[8];
+        for (int k = 0; k < 8; k++) in[k] = DCAC[k * 8 + c];
+        fllm8(in, sum, rot);
+        DCAC[0 * 8 + c] = (int16_t)fdescale(sum[0], 5);
+        DCAC[4 * 8 + c] = (int16_t)fdescale(sum[1], 5);
+        for (int k = 1; k < 8; k++) if (k != 4) DCAC[k * 8 + c] = (int16_t)fdescale(rot[k], 18);
+    }
+}
+
+/* DOUBLE_QUANTIZE, LIB/encoder/quantize.c:16: (DCTELEM) round((double)x / (double)q), C round() =
+ * half away from zero.  Restated in integers (exact: a quotient that is not a half-integer is at least
+ * 1/(2q) away from one, far more than a double rounding error). */
+static inline int16_t quant1(int16_t x, int16_t q) {
+    const int32_t a = x < 0 ? -(int32_t)x : (int32_t)x, d = q < 0 ? -(int32_t)q : (int32_t)q;
+    const int32_t m = (2 * a + d) / (2 * d);
+    return (int16_t)(((x < 0) != (q < 0)) ? -m : m);
+}
+/* quantize.c:18-31.  prev = DC level of the previous block of the plane. */
+void orc_quantize_I(int16_t* prev, const int16_t* quant, const int16_t* DCAC, int16_t* DCACq, int16_t* DCACq_next) {
+    const int16_t dc = quant1(DCAC[0], quant[0]);
+    DCACq[0] = (int16_t)(dc - *prev);
+    *prev = dc;
+    DCACq_next[0] = dc;
+    for (int k = 1; k < 64; k++) DCACq_next[k] = DCACq[k] = quant1(DCAC[k], quant[k]);
+}
+/* quantize.c:33-42. */
+void orc_quantize_P(const int16_t* quant, int16_t* DCACq_prev, const int16_t* DCAC, int16_t* DCACq) {
+    for (int k = 0; k < 64; k++) {
+        const int16_t v = quant1(DCAC[k], quant[k]);
+        DCACq[k] = (int16_t)(v - DCACq_prev[k]);
+        DCACq_prev[k] = v;
+    }
+}
+
+/* LIB/encoder/lossless_encode.c:30-138.  MSB-first bit writer; returns the stream length in bytes.
+ * fix_tail == 0 reproduces output_rest() (:80-83), which stores the LOW byte of the bit buffer (always
+ * zero) instead of the pending top byte: the last partial byte of the stream is 0. */
+typedef struct { uint8_t* p; uint64_t bits; uint32_t acc; int nacc; } bitwr_t;
+static inline void put_bits(bitwr_t* w, int n, uint32_t v) {
+    for (int i = n - 1; i >= 0; i--) {
+        w->acc = (w->acc << 1) | ((v >> i) & 1u);
+        if (++w->nacc == 8) { w->p[w->bits >> 3] = (uint8_t)w->acc; w->acc = 0; w->nacc = 0; }
+        w->bits++;
+    }
+}
+static inline uint32_t vli_enc(int32_t x, uint32_t* size) {          /* encode_VLI :121-138 */
+    uint32_t a = (uint32_t)(x < 0 ? -x : x), s = 0;
+    while (s < 11 && a >> s) s++;                                    /* sizes are capped at 11 (:135) */
+    *size = s;
+    return x > 0 ? (uint32_t)x : (((uint32_t)(x - 1)) & (s ? (0xFFFFFFFFu >> (32 - s)) : 0u));
+}
+uint32_t orc_lossless_encode(int num_blocks, const int16_t* DCACq, uint8_t* bitstream, int fix_tail) {
+    const uint8_t* zz = orc_zigzag();
+    bitwr_t w = {bitstream, 0, 0, 0};
+    for (int b = 0; b < num_blocks; b++) {
+        const int16_t* dct = DCACq + (size_t)b * 64;
+        uint32_t size, amp = vli_enc(dct[0], &size);
+        put_bits(&w, 4, size);                                        /* output_DC :86-96 */
+        put_bits(&w, (int)size, amp);
+        int last = 63;
+        while (last > 0 && dct[zz[last]] == 0) last--;
+        int idx = 1;
+        while (idx <= last) {
+            int run = 0;
+            while (run < 16 && dct[zz[idx]] == 0) { run++; idx++; }
+            if (run == 16) { put_bits(&w, 8, 0xF0); }                 /* output_ZRL */
+            else {
+                amp = vli_enc(dct[zz[idx]], &size);
+                put_bits(&w, 4, (uint32_t)run);
+                put_bits(&w, 4, size);
+                put_bits(&w, (int)size, amp);
+                idx++;
+            }
+        }
+        if (last < 63) put_bits(&w, 8, 0);                            /* output_END */
+    }
+    if (w.nacc) w.p[w.bits >> 3] = fix_tail ? (uint8_t)(w.acc << (8 - w.nacc)) : 0;
+    return (uint32_t)((w.bits + 7) >> 3);
+}

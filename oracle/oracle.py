@@ -72,6 +72,13 @@ class Checker:
         self._frame.restype = None
         self._mpg.argtypes = [p, C.c_size_t, C.c_uint32, C.c_uint32, p, p, p, C.c_int, p]
         self._mpg.restype = C.c_int
+        self._enc = L.ref_encode_mpg if is_ref else L.orc_encode_mpg
+        self._enc.argtypes = [p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, p, p, C.c_int, p, C.c_size_t, p]
+        self._enc.restype = C.c_int
+        if is_ref:
+            L.ref_encode_mpg_files.argtypes = [p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, p,
+                                               C.c_size_t, p]
+            L.ref_encode_mpg_files.restype = C.c_int
 
     # -- stage functions -------------------------------------------------------------------------
     def lossless_decode(self, num_blocks: int, bitstream, quant, P: int = 0, DCACq: np.ndarray | None = None):
@@ -119,6 +126,39 @@ class Checker:
         if rc != 0:
             raise RuntimeError(f"{self.kind} decode_mpg failed rc={rc}")
         return out
+
+    # -- encoder: the frame loop of LIB/encoder/mjpeg423_encoder.c:97-225 -------------
+    @staticmethod
+    def encode_bound(n: int, W: int, H: int) -> int:
+        return 20 + n * (16 + 3 * (W // 8) * (H // 8) * 160 + 8 + 8) + 512
+
+    def encode_mpg(self, frames: np.ndarray, max_I_interval: int = 1, yq=None, cq=None, fix_tail: bool = False) -> np.ndarray:
+        """frames: (n, H, W, 4) uint8 BGRA -> the .mpg bytes (the last 512 are the zeroed pad)."""
+        fr = np.ascontiguousarray(frames, dtype=np.uint8)
+        n, H, W, _ = fr.shape
+        out = np.zeros(self.encode_bound(n, W, H), dtype=np.uint8)
+        ln = C.c_size_t(0)
+        yqa = None if yq is None else np.ascontiguousarray(yq, dtype=np.int16)
+        cqa = None if cq is None else np.ascontiguousarray(cq, dtype=np.int16)
+        rc = self._enc(fr.ctypes.data, n, W, H, max_I_interval, None if yqa is None else yqa.ctypes.data,
+                       None if cqa is None else cqa.ctypes.data, int(fix_tail), out.ctypes.data, out.size, C.byref(ln))
+        if rc:
+            raise RuntimeError(f"{self.kind} encode_mpg failed rc={rc}")
+        return out[:ln.value].copy()
+
+    def encode_mpg_files(self, frames: np.ndarray, max_I_interval: int, tmpdir: str) -> np.ndarray:
+        """The reference's own mjpeg423_encode() through BMP files in tmpdir (ref only).  The last 512 bytes of
+        the result are uninitialised stack of the reference: compare [:-512]."""
+        assert self.is_ref
+        fr = np.ascontiguousarray(frames, dtype=np.uint8)
+        n, H, W, _ = fr.shape
+        out = np.zeros(self.encode_bound(n, W, H), dtype=np.uint8)
+        ln = C.c_size_t(0)
+        rc = self.lib.ref_encode_mpg_files(fr.ctypes.data, n, W, H, max_I_interval, tmpdir.encode(), out.ctypes.data,
+                                           out.size, C.byref(ln))
+        if rc:
+            raise RuntimeError(f"ref_encode_mpg_files failed rc={rc}")
+        return out[:ln.value].copy()
 
     # -- reference encoder pieces (ref only; used to cross-check the from-spec encoder) ------------
     def lossless_encode(self, levels: np.ndarray) -> bytes:
