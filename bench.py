@@ -37,6 +37,9 @@ WORKLOADS = {
     "4k": (3840, 2160, 256, 16, 256, "default", False),         # BASELINE configs[3]: dense, entropy-bound
     "4k-q1": (3840, 2160, 64, 8, 256, "ones", False),           # configs[3] extreme: all-ones quant tables
     "1080p-8192": (1920, 1080, 8192, 64, 16, "default", True),  # BASELINE configs[4]: fixed total, sharded
+    # SURVEY.md 8f3 (next row): the ENCODER, frames -> .mpg.  Not a BASELINE config; reported with its own metric.
+    "enc-1080p": (1920, 1080, 256, 32, 16, "default", False),
+    "enc-480p": (640, 480, 1024, 32, 16, "default", False),
 }
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
@@ -63,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)],
+                                          "-lms", "50", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -157,10 +160,139 @@ def reference_arm(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+def procedural_frames(W: int, H: int, n: int, uniq: int, amp: int) -> np.ndarray:
+    """(n, H, W, 4) BGRA: `uniq` procedural pictures (gradients + LCG-free numpy noise) cycled."""
+    rng = np.random.default_rng(0x423)
+    y, x = np.mgrid[0:H, 0:W]
+    base = np.zeros((uniq, H, W, 4), np.uint8)
+    for f in range(uniq):
+        g = np.stack([(255 * (x + y) // (W + H) + f) & 255, (255 * y // H + f) & 255, (255 * x // W + f) & 255], -1)
+        base[f, ..., :3] = (g + rng.integers(0, max(amp, 1), size=(H, W, 3))) & 255
+    return base[np.arange(n) % uniq]
+
+
+def encoder_bench(args, rank: int, world: int, local_rank: int):
+    """encoded frames/s of mjpeg423_b200_encode_frames (frames -> complete .mpg in host memory).
+    `value`: frames already resident in HBM; `e2e`: pinned host frames in.  --impl reference: the reference's own
+    encoder functions (oracle/_ref frame loop, else the restatement), one clip per host core."""
+    W, H, frames, uniq, amp, _, _ = WORKLOADS[args.workload]
+    if args.frames:
+        frames = args.frames
+    cores = os.cpu_count() or 1
+    max_i = 24                                   # COMMON/config.h:54
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import threading
+        from oracle import oracle
+        chk = oracle.best()
+        per = 4 if H >= 1080 else 16
+        clip = procedural_frames(W, H, per, per, amp)
+        def work():
+            chk.encode_mpg(clip, max_i)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            th = [threading.Thread(target=work) for _ in range(cores)]
+            [t.start() for t in th]
+            [t.join() for t in th]
+        dt = time.perf_counter() - t0
+        fps = per * cores * args.steps / dt
+        print(json.dumps({"impl": "reference", "metric": "encoded frames/sec", "value": fps, "unit": "frames/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32",
+                          "data": "synthetic", "config": {"workload": args.workload, "width": W, "height": H, "max_I_interval": max_i},
+                          "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": chk.kind,
+                                           "sample": f"{cores} threads x {per}-frame clip per step"},
+                          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+    import torch
+    import torch.distributed as dist
+    import mjpeg423_b200
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    fr = procedural_frames(W, H, frames, uniq, amp)
+    dec = mjpeg423_b200.Decoder(local_rank)
+    d = dec.device_alloc(fr.nbytes)
+    dec.to_device(d, fr)
+    mpg = dec.encode_frames(None, max_i, d_frames=d, shape=(frames, H, W))
+    verified = None
+    if not args.no_verify:
+        from oracle import oracle
+        chk = oracle.best()
+        k = 6
+        want = chk.encode_mpg(fr[:k], max_i)
+        body = int(want[16:20].view("<u4")[0])           # payload bytes of the k-frame file = prefix of the long one
+        if not np.array_equal(mpg[20:20 + body], want[20:20 + body]):
+            raise SystemExit("encoder output differs from the oracle -- refusing to report a number")
+        verified = f"frame records of the first {k} frames byte-identical to the {chk.kind} encoder"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        dec.encode_frames(None, max_i, d_frames=d, shape=(frames, H, W))
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        dec.encode_frames(None, max_i, d_frames=d, shape=(frames, H, W))
+        st = dec.stats()
+        ev_ms += st["total_ms"]
+        launches += st["kernel_launches"]
+    barrier()
+    clocks = sampler.stop()
+    pin = dec.pinned(fr.nbytes)
+    pin.array[:] = fr.reshape(-1)
+    host_frames = pin.array.reshape(fr.shape)
+    dec.encode_frames(host_frames, max_i)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        out = dec.encode_frames(host_frames, max_i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    (ev_ms_max, e2e_s_max), (total_frames, total_launches) = reduce_over_ranks(dist, [ev_ms, e2e_s], [frames, launches], "cuda")
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        fps = total_frames * args.steps / (ev_ms_max / 1e3)
+        P = W * H
+        # algorithmic bytes per frame: read 4P pixels, write and re-read 6P of levels (size + emit passes), write C
+        alg = 4 * P + 3 * 6 * P + mpg.size / frames
+        line = {"metric": "encoded frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
+                "config": {"workload": args.workload, "width": W, "height": H, "frames_per_gpu": frames, "unique_pictures": uniq,
+                           "noise_amp": amp, "max_I_interval": max_i, "compressed_bytes_per_frame": mpg.size / frames,
+                           "p_frames": int(mjpeg423_b200.probe(mpg).num_pframes), "verified": verified,
+                           "l2": "inputs larger than L2 (%.1f GB of frames per step)" % (fr.nbytes / 1e9),
+                           "timing": "cuda events (whole call incl. the .mpg read-back), max over ranks"},
+                "clocks": clocks,
+                "e2e": {"value": total_frames * e2e_steps / e2e_s_max, "unit": "frames/s", "h2d_bytes_per_step": int(fr.nbytes),
+                        "d2h_bytes_per_step": int(out.size), "api": "mjpeg423_b200_encode_frames (pinned host frames in, host .mpg out)"},
+                "gpu_launches": int(total_launches),
+                "roofline": {"bound": "hbm", "kernel": "encoder pipeline (k_enc_transform/size/scan/emit)", "achieved": fps / world * alg / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": fps / world * alg / 1e9 / peak, "traffic": None,
+                             "peak_source": peak_src, "algorithmic_bytes_per_frame": alg},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    pin.free()
+    dec.device_free(d)
+    dec.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
@@ -176,6 +308,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload.startswith("enc-"):
+        encoder_bench(args, rank, world, local_rank)
+        return
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
@@ -295,7 +430,8 @@ def main():
             # 4 bytes per coded coefficient, the block index 8 bytes per block, per-segment state 16 bytes
             "entropy_sync": {"ms": ps["sync_ms"], "bytes": payload_bytes + 12 * ps["segments"], "kernels": "k_entropy_sync"},
             "entropy_chain": {"ms": ps["chain_ms"], "bytes": 16 * ps["segments"], "kernels": "k_entropy_chain"},
-            "entropy_index": {"ms": ps["index_ms"], "bytes": payload_bytes + lists + 8 * blocks, "kernels": "k_entropy_index"},
+            "entropy_index": {"ms": ps["index_ms"], "bytes": payload_bytes + lists + 8 * blocks + 20 * ps["segments"],
+                              "kernels": "k_entropy_index"},      # (+ the tiny k_entropy_dcscan, timed with it)
             "decode_fused": {"ms": ps["decode_ms"], "bytes": lists + 8 * blocks + 4 * P * n, "kernels": "k_decode_fused"},
         }
         for s in stage.values():
@@ -315,7 +451,7 @@ def main():
         roofline = {"bound": "hbm", "kernel": stage[dom]["kernels"], "achieved": stage[dom]["GBs"], "peak": peak,
                     "unit": "GB/s", "frac": stage[dom]["GBs"] / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_step": stage[dom]["bytes"], "step_ms_in_kernel": stage[dom]["ms"],
-                    "launches_per_step": ps["kernel_launches"] // 4,
+                    "launches_per_step": ps["kernel_launches"] // 5,     # one per pipeline chunk
                     "pipeline_headline": {"bytes_per_frame": Cbar + 4 * P, "GBs": fps / world * (Cbar + 4 * P) / 1e9,
                                           "frac": fps / world * (Cbar + 4 * P) / 1e9 / peak}}
         cpu_baseline = None

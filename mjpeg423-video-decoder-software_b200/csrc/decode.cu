@@ -179,7 +179,7 @@ k_decode_fused(const uint2* __restrict__ blk_info,
     };
     // The head of every plane's first run (4 x 32 luminance entries, 32 of each chrominance plane: most of a
     // tile at the usual rates) is fetched one tile ahead as well, behind the IDCTs of the current tile.
-    constexpr int PRE_Y = 4;
+    constexpr int PRE_Y = 8;
     uint2 ninfo[3];
     uint32_t npreY[PRE_Y], npreC[2];
     auto prefetch_lists = [&]() {
