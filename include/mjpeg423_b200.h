@@ -201,6 +201,36 @@ int mjpeg423_b200_encode_frames(mjpeg423_b200_ctx* ctx, const void* frames, int 
                                 uint32_t w_size, uint32_t h_size, uint32_t max_I_interval, uint32_t flags,
                                 uint8_t* mpg, size_t cap, size_t* mpg_len);
 
+/* ---- 5. display side: C0/libs/ece423_vid_ctl/ece423_vid_ctl.h:67-77, C0/playback.c ---- */
+/* The reference's N-buffer frame ring with the mSGDMA/HDMI parts removed: buffers are pinned host memory (plain
+ * memory without a CUDA device), "scan-out" is get_displayed_buffer().  Same state machine and return values as
+ * ece423_video_display_{init, register_written_buffer, buffer_is_available, switch_frames, get_buffer,
+ * clear_screen}: buffer_is_available() returns 0 when the producer's slot is free and -1 while it is on screen;
+ * switch_frames() returns 0 after flipping to a newer frame and -1 when there is none.  num_buffers is clamped to
+ * [2, 25] like the reference and rounded down to a power of two (the indices are masked, config.h:27). */
+#define MJPEG423_DISPLAY_MAX_BUFFERS 25
+typedef struct mjpeg423_b200_display mjpeg423_b200_display;
+mjpeg423_b200_display* mjpeg423_b200_display_init(int width, int height, int num_buffers);
+void  mjpeg423_b200_display_free(mjpeg423_b200_display* display);
+void  mjpeg423_b200_display_register_written_buffer(mjpeg423_b200_display* display);
+int   mjpeg423_b200_display_buffer_is_available(mjpeg423_b200_display* display);
+int   mjpeg423_b200_display_switch_frames(mjpeg423_b200_display* display);
+void* mjpeg423_b200_display_get_buffer(mjpeg423_b200_display* display);            /* the producer's slot */
+void* mjpeg423_b200_display_get_displayed_buffer(mjpeg423_b200_display* display);  /* the slot on screen */
+void  mjpeg423_b200_display_clear_screen(mjpeg423_b200_display* display, char color);
+int   mjpeg423_b200_display_num_buffers(const mjpeg423_b200_display* display);
+/* The playback loop of C0/playback.c with the GPU decoder as producer: frames [first, first+n) go through the ring
+ * and are displayed every frame_period_us (41666 = the reference's 24 fps, COMMON/config.h:29; 0 = the reference's
+ * noTimer mode: flip after every frame).  on_display (may be NULL) sees every displayed frame in order.  Returns
+ * the number of frames displayed (n) or a negative MJPEG423_E_*; *dropped (may be NULL) = timer ticks without a new
+ * frame. */
+long mjpeg423_b200_play(mjpeg423_b200_ctx* ctx, const uint8_t* mpg, size_t len, uint32_t first, uint32_t n,
+                        mjpeg423_b200_display* display, uint32_t frame_period_us,
+                        void (*on_display)(void* user, uint32_t frame_index, const rgb_pixel_t* frame), void* user,
+                        uint32_t* dropped);
+/* encode_bmp(), LIB/libbmp/encode_bmp.c:7-25: one 32-bpp bottom-up BMP, byte-identical to the reference's file. */
+int mjpeg423_b200_write_bmp(const char* path, const rgb_pixel_t* rgb, uint32_t w_size, uint32_t h_size);
+
 #ifdef __cplusplus
 }
 #endif

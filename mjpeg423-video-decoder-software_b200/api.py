@@ -51,7 +51,14 @@ EXPORTS = [
     "mjpeg423_b200_device_free", "mjpeg423_b200_memcpy_d2h", "mjpeg423_b200_memcpy_h2d", "mjpeg423_b200_sync",
     "mjpeg423_b200_device_count", "mjpeg423_b200_hash_frames",
     "mjpeg423_b200_encode_bound", "mjpeg423_b200_encode_frames",
+    "mjpeg423_b200_display_init", "mjpeg423_b200_display_free", "mjpeg423_b200_display_register_written_buffer",
+    "mjpeg423_b200_display_buffer_is_available", "mjpeg423_b200_display_switch_frames", "mjpeg423_b200_display_get_buffer",
+    "mjpeg423_b200_display_get_displayed_buffer", "mjpeg423_b200_display_clear_screen", "mjpeg423_b200_display_num_buffers",
+    "mjpeg423_b200_play", "mjpeg423_b200_write_bmp",
 ]
+
+
+DISPLAY_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_void_p)     # on_display(user, frame_index, frame)
 
 
 class _Info(C.Structure):
@@ -139,6 +146,17 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "mjpeg423_b200_hash_frames": (i32, [p, p, u64, u32, p]),
         "mjpeg423_b200_encode_bound": (sz, [u32, u32, u32]),
         "mjpeg423_b200_encode_frames": (i32, [p, p, i32, u32, u32, u32, u32, u32, p, sz, C.POINTER(sz)]),
+        "mjpeg423_b200_display_init": (p, [i32, i32, i32]),
+        "mjpeg423_b200_display_free": (None, [p]),
+        "mjpeg423_b200_display_register_written_buffer": (None, [p]),
+        "mjpeg423_b200_display_buffer_is_available": (i32, [p]),
+        "mjpeg423_b200_display_switch_frames": (i32, [p]),
+        "mjpeg423_b200_display_get_buffer": (p, [p]),
+        "mjpeg423_b200_display_get_displayed_buffer": (p, [p]),
+        "mjpeg423_b200_display_clear_screen": (None, [p, C.c_char]),
+        "mjpeg423_b200_display_num_buffers": (i32, [p]),
+        "mjpeg423_b200_play": (C.c_long, [p, p, sz, u32, u32, p, u32, DISPLAY_CB, p, C.POINTER(u32)]),
+        "mjpeg423_b200_write_bmp": (i32, [C.c_char_p, p, u32, u32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -415,3 +433,71 @@ def frame_hash_host(frames: np.ndarray) -> np.ndarray:
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
         z = z ^ (z >> np.uint64(31))
         return z.sum(axis=1, dtype=np.uint64)
+
+
+# ---- display side: the reference's frame ring, ece423_vid_ctl.h:67-77 ---------------------------
+class Display:
+    """N-buffer frame ring (pinned host memory when a CUDA device exists, plain memory otherwise)."""
+
+    def __init__(self, width: int, height: int, num_buffers: int = 4):
+        self.lib = load_library()
+        self.h = self.lib.mjpeg423_b200_display_init(width, height, num_buffers)
+        if not self.h:
+            raise RuntimeError("display_init failed: " + _err(self.lib))
+        self.width, self.height = width, height
+        self.num_buffers = self.lib.mjpeg423_b200_display_num_buffers(self.h)
+
+    def _view(self, ptr: int) -> np.ndarray:
+        buf = (C.c_uint8 * (self.width * self.height * 4)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(self.height, self.width, 4)
+
+    def register_written_buffer(self) -> None:
+        self.lib.mjpeg423_b200_display_register_written_buffer(self.h)
+
+    def buffer_is_available(self) -> int:
+        return self.lib.mjpeg423_b200_display_buffer_is_available(self.h)
+
+    def switch_frames(self) -> int:
+        return self.lib.mjpeg423_b200_display_switch_frames(self.h)
+
+    def get_buffer(self) -> np.ndarray:
+        return self._view(self.lib.mjpeg423_b200_display_get_buffer(self.h))
+
+    def get_displayed_buffer(self) -> np.ndarray:
+        return self._view(self.lib.mjpeg423_b200_display_get_displayed_buffer(self.h))
+
+    def clear_screen(self, color: int = 0) -> None:
+        self.lib.mjpeg423_b200_display_clear_screen(self.h, bytes([color & 255]))
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.mjpeg423_b200_display_free(self.h)
+            self.h = None
+
+
+def play(dec: "Decoder", mpg, display: Display, first: int = 0, n: int | None = None, frame_period_us: int = 0,
+         on_display=None) -> tuple[int, int]:
+    """C0/playback.c's loop: decode frames [first, first+n) through the ring; on_display(frame_index, frame ndarray)
+    is called for every displayed frame.  Returns (frames displayed, timer ticks without a new frame)."""
+    a = _bytes_arr(mpg)
+    if n is None:
+        n = probe(a).num_frames - first
+    H, W = display.height, display.width
+
+    def cb(_user, idx, ptr):
+        if on_display is not None:
+            buf = (C.c_uint8 * (W * H * 4)).from_address(ptr)
+            on_display(idx, np.frombuffer(buf, dtype=np.uint8).reshape(H, W, 4))
+    ccb = DISPLAY_CB(cb)
+    dropped = C.c_uint32(0)
+    rc = dec.lib.mjpeg423_b200_play(dec.h, a.ctypes.data, a.size, first, n, display.h, frame_period_us, ccb, None, C.byref(dropped))
+    if rc < 0:
+        _check(dec.lib, int(rc), "play")
+    return int(rc), int(dropped.value)
+
+
+def write_bmp(path: str, frame: np.ndarray) -> None:
+    """encode_bmp(), LIB/libbmp/encode_bmp.c: 32-bpp BMP of one (H, W, 4) BGRA frame (host-only function)."""
+    lib = load_library()
+    fr = np.ascontiguousarray(frame, dtype=np.uint8)
+    _check(lib, lib.mjpeg423_b200_write_bmp(os.fsencode(path), fr.ctypes.data, fr.shape[1], fr.shape[0]), "write_bmp")

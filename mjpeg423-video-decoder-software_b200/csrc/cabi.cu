@@ -153,16 +153,7 @@ void accel_submit(int plane, void* buf, uint32_t bytes) {
 }
 
 void write_bmp32(const char* path, const uint8_t* bgra, uint32_t W, uint32_t H) {
-    FILE* f = std::fopen(path, "wb");
-    if (!f) { set_error(std::string("cannot open ") + path); die("mjpeg423_decode"); }
-    const uint32_t img = W * H * 4, off = 54, size = off + img;
-    uint8_t h[54] = {'B', 'M'};
-    auto p32 = [&](int at, uint32_t v) { h[at] = (uint8_t)v; h[at + 1] = (uint8_t)(v >> 8); h[at + 2] = (uint8_t)(v >> 16); h[at + 3] = (uint8_t)(v >> 24); };
-    p32(2, size); p32(10, off); p32(14, 40); p32(18, W); p32(22, H);
-    h[26] = 1; h[28] = 32; p32(34, img); p32(38, 2835); p32(42, 2835);
-    std::fwrite(h, 1, 54, f);
-    for (uint32_t y = 0; y < H; y++) std::fwrite(bgra + (size_t)(H - 1 - y) * W * 4, 1, (size_t)W * 4, f);  // bottom-up
-    std::fclose(f);
+    if (mjpeg423_b200_write_bmp(path, reinterpret_cast<const rgb_pixel_t*>(bgra), W, H) != MJPEG423_OK) die("mjpeg423_decode");
 }
 
 }  // namespace

@@ -21,7 +21,7 @@ def lib():
 def test_header_symbols_are_exported(lib):
     hdr = open(os.path.join(ROOT, "include", "mjpeg423_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", hdr)) - {"defined", "sizeof"}
+    declared = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", hdr)) - {"defined", "sizeof", "void"}   # "void (" = a function-pointer parameter
     declared |= {"Yquant", "Cquant", "zigzag_table"}
     declared = {d for d in declared if not d.isupper() and not d.endswith("_t")}
     assert declared == set(api.EXPORTS), declared ^ set(api.EXPORTS)
