@@ -60,8 +60,9 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     int rc;
     if ((rc = s_in.reserve(len + 64))) return rc;
     if ((rc = s_tab.reserve(256 + 256))) return rc;
-    if ((rc = s_seg.reserve((size_t)sd.nseg * 24 + 96))) return rc;
-    if ((rc = s_idx.reserve((size_t)num_blocks * 8 + (size_t)sd.nseg * SYM_STRIDE * 4 + 128))) return rc;
+    const uint32_t nseg_pad = (sd.nseg + SUPER - 1) / SUPER * SUPER;      // global segment numbering is SUPER-aligned
+    if ((rc = s_seg.reserve((size_t)nseg_pad * 24 + 96))) return rc;
+    if ((rc = s_idx.reserve((size_t)num_blocks * 8 + (size_t)nseg_pad * SYM_STRIDE * 4 + 128))) return rc;
     if ((rc = s_mid.reserve(coef_bytes))) return rc;
     uint8_t* tab = s_tab.as<uint8_t>();
     int16_t* d_q = reinterpret_cast<int16_t*>(tab);                  // 128 int16 (table 0 used)
@@ -75,15 +76,15 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     j.d_payload = s_in.as<uint8_t>();
     j.d_streams = d_sd;
     j.stream_lo = 0; j.n_streams = 1;
-    j.seg_lo = 0; j.seg_hi = sd.nseg;
+    j.seg_lo = 0; j.seg_hi = nseg_pad;
     uint32_t* seg = s_seg.as<uint32_t>();
-    CUX(cudaMemsetAsync(seg + 5 * (size_t)sd.nseg, 0, (size_t)sd.nseg * 4, s));   // every segment belongs to stream 0
-    j.d_seg_stream = seg + 5 * (size_t)sd.nseg;
-    j.d_seg_entry = seg; j.d_seg_exit = seg + sd.nseg; j.d_seg_cnt = seg + 2 * (size_t)sd.nseg;
-    j.d_seg_first = seg + 3 * (size_t)sd.nseg;
-    j.d_seg_dc = seg + 4 * (size_t)sd.nseg;
-    j.d_stream_blocks = seg + 6 * (size_t)sd.nseg;
-    j.d_fixups = reinterpret_cast<unsigned long long*>(seg + ((6 * (size_t)sd.nseg + 3) & ~(size_t)1));
+    CUX(cudaMemsetAsync(seg + 5 * (size_t)nseg_pad, 0, (size_t)nseg_pad * 4, s));   // every segment belongs to stream 0
+    j.d_seg_stream = seg + 5 * (size_t)nseg_pad;
+    j.d_seg_entry = seg; j.d_seg_exit = seg + nseg_pad; j.d_seg_cnt = seg + 2 * (size_t)nseg_pad;
+    j.d_seg_first = seg + 3 * (size_t)nseg_pad;
+    j.d_seg_dc = seg + 4 * (size_t)nseg_pad;
+    j.d_stream_blocks = seg + 6 * (size_t)nseg_pad;
+    j.d_fixups = reinterpret_cast<unsigned long long*>(seg + ((6 * (size_t)nseg_pad + 3) & ~(size_t)1));
     j.d_blk_info = s_idx.as<uint2>();
     j.d_sym = s_idx.as<uint32_t>() + ((2 * (size_t)num_blocks + 7) & ~(size_t)7);
     j.sym_seg0 = 0;

@@ -17,6 +17,8 @@ constexpr int SEG_BYTES = 512;
 constexpr int SEG_BITS = SEG_BYTES * 8;
 constexpr int CP_BITS = 512;
 constexpr int NCP = SEG_BITS / CP_BITS;        // checkpoints per segment (the last one is the segment end)
+constexpr int SUPER = 4;                       // segments parsed by one lane of the synchronisation pass; every stream's
+                                               // range of global segment numbers is padded to a multiple of it
 constexpr int ENT_TPB = 128;                   // threads per CTA in the entropy kernels
 constexpr int MIN_BLOCK_BITS = 12;             // DC size 0 + END
 constexpr uint32_t RUNAWAY_BITS = 8192;        // parse guard for non-conforming / speculative garbage

@@ -181,10 +181,11 @@ k_decode_fused(const uint2* __restrict__ blk_info,
     // tile at the usual rates) is fetched one tile ahead as well, behind the IDCTs of the current tile.
     constexpr int PRE_Y = 8;
     uint2 ninfo[3];
-    uint32_t npreY[PRE_Y], npreC[2];
+    uint32_t npreY[PRE_Y], npreC[2], npred[3];
     auto prefetch_lists = [&]() {
 #pragma unroll
         for (int p = 0; p < 3; p++) {
+            npred[p] = ninfo[p].x == BLK_NO_SEG ? 0u : __ldg(seg_dc + ninfo[p].x / SYM_STRIDE);   // DC predictor of the block's segment
             uint32_t r0, r1, rest;
             first_run(ninfo[p].x, ninfo[p].x + (ninfo[p].y >> 16), r0, r1, rest);
             if (p == 0) {
@@ -207,7 +208,10 @@ k_decode_fused(const uint2* __restrict__ blk_info,
 
         uint32_t meta[3], lx[3], lxe[3], preY[PRE_Y], preC[2];
 #pragma unroll
-        for (int p = 0; p < 3; p++) { lx[p] = ninfo[p].x; lxe[p] = ninfo[p].x + (ninfo[p].y >> 16); meta[p] = absolute_dc(ninfo[p], seg_dc); }
+        for (int p = 0; p < 3; p++) {
+            lx[p] = ninfo[p].x; lxe[p] = ninfo[p].x + (ninfo[p].y >> 16);
+            meta[p] = (ninfo[p].y & 0xFFFF0000u) | ((ninfo[p].y + npred[p]) & 0xFFFFu);          // absolute DC level
+        }
 #pragma unroll
         for (int i = 0; i < PRE_Y; i++) preY[i] = npreY[i];
         preC[0] = npreC[0]; preC[1] = npreC[1];

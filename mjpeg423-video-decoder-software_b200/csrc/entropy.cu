@@ -70,29 +70,41 @@ __device__ __forceinline__ uint32_t parse_segment(const uint8_t* base, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Speculative parse + merge.  CTA c handles SYNC_SLOTS consecutive global segments: slot 0 is the
-// segment BEFORE its SYNC_OWN own ones (halo), so that slot 1 has a predecessor exit without any
-// inter-CTA dependency.  A slot's predecessor is the previous slot unless the segment is the first of
-// its stream.
+// Speculative parse + merge.  A LANE parses a SUPER-segment: SUPER consecutive segments of one stream
+// (every stream's global segment range is padded to a multiple of SUPER, so super u = global segments
+// [u*SUPER, (u+1)*SUPER)).  Only the first few hundred bits of a lane's parse are ever on the wrong
+// trajectory, so the longer the lane's run, the smaller the share of re-parsing: with SUPER = 4 the
+// merge phase costs ~8 % of the parse instead of ~30 % with one segment per lane.
 //
-// Phase B: a segment whose true entry E (the predecessor's exit) is not where the speculation started is
-// a MERGE JOB: parse from E until the trajectory meets the recorded one (tested at the first block start
-// at or after every checkpoint boundary -- once merged, that IS the checkpoint).  Jobs are short (a few
-// hundred bits) and of very uneven length; pulled per lane from the CTA's pool they keep the lanes busy.
+// CTA c handles SYNC_OWN consecutive supers + the one BEFORE them (slot 0, halo), so that slot 1 has a
+// predecessor exit without any inter-CTA dependency.
+//
+// Phase A: every lane parses its super from its first bit as if a block started there, recording the first
+// block start at or after NCK checkpoint boundaries -- every CP_BITS inside the first segment (where
+// merges happen), then every segment boundary -- with the number of blocks started before it.
+// Phase B: the predecessor's speculative exit is the lane's true entry E; parse from E until the
+// trajectory meets the recorded one (equal position at a block start => identical future; tested at the
+// first block start past each boundary -- once merged, that IS the checkpoint).  The segment boundaries
+// passed before the merge are recorded from the true trajectory, the later ones follow from the
+// checkpoints.  Round 2 repeats this for lanes whose predecessor's exit moved in round 1.
 // ------------------------------------------------------------------------------------------------
-constexpr int SYNC_SLOTS = 512;
-constexpr int SYNC_OWN = SYNC_SLOTS - 1;
-constexpr int SYNC_PER_THREAD = SYNC_SLOTS / ENT_TPB;
+constexpr int NCK = NCP + SUPER - 1;                    // checkpoints of a super (the last NCK - NCP + 1 are segment boundaries)
+constexpr int SYNC_OWN = ENT_TPB - 1;
+constexpr uint32_t SUPER_BITS = SUPER * SEG_BITS;
 constexpr uint32_t NO_WORK = 0xFFFFFFFFu;
 
+// Offset of checkpoint boundary i from the super's first bit, and the checkpoint index of segment boundary j (1..SUPER).
+__device__ __forceinline__ uint32_t ck_bnd(uint32_t i) { return i < (uint32_t)NCP ? (i + 1u) * CP_BITS : (i - (NCP - 2u)) * SEG_BITS; }
+__device__ __forceinline__ uint32_t ck_of_seg(uint32_t j) { return (uint32_t)NCP - 2u + j; }
+// Index of the last checkpoint boundary at or before offset `rel` (rel >= CP_BITS).
+__device__ __forceinline__ uint32_t ck_last(uint32_t rel) {
+    return rel < (uint32_t)SEG_BITS ? rel / CP_BITS - 1u : min((uint32_t)NCK - 1u, rel / SEG_BITS + (NCP - 2u));
+}
+
 struct SyncShared {
-    uint32_t cp[NCP][SYNC_SLOTS];  // checkpoint j: (first block start >= seg_start + (j+1)*CP_BITS, minus seg_start) << 16
-                                   //               | blocks started before it
-    uint32_t E[SYNC_SLOTS];        // entry (f position) the result below was resolved for
-    uint32_t rexit[SYNC_SLOTS];    // resolved exit (f position)
-    uint32_t rcnt[SYNC_SLOTS];     // resolved block count
-    uint32_t job[SYNC_SLOTS];      // pool of slots to resolve by parsing
-    uint32_t njobs, next;
+    uint32_t cp[NCK][ENT_TPB];         // (first block start >= boundary i, minus the super's first bit) << 16 | blocks before it
+    uint32_t tpos[SUPER + 1][ENT_TPB]; // resolved: first block start >= segment boundary j (tpos[0] = the entry E)
+    uint32_t tcnt[SUPER + 1][ENT_TPB]; // resolved: blocks started before it, counted from E
 };
 
 // Where a global segment lives.
@@ -116,45 +128,51 @@ __device__ __forceinline__ SegCtx seg_ctx(const uint8_t* __restrict__ payload, c
     return c;
 }
 
-// Resolve slot k for entry E without parsing where possible; returns false when it needs a merge job.
-__device__ __forceinline__ bool resolve_trivial(SyncShared& sh, uint32_t k, uint32_t E, uint32_t seg_start, uint32_t fstop_eos) {
-    const uint32_t last = sh.cp[NCP - 1][k];
-    const uint32_t spec_exit = seg_start + (last >> 16), spec_cnt = last & 0xFFFFu;
-    sh.E[k] = E;
-    if (E >= seg_start + SEG_BITS || E >= fstop_eos) { sh.rexit[k] = E; sh.rcnt[k] = 0; return true; }   // owns nothing
-    if (E == seg_start) { sh.rexit[k] = spec_exit; sh.rcnt[k] = spec_cnt; return true; }                 // speculation was right
-    if (E >= seg_start + CP_BITS) {                      // E itself may be a recorded block start
-        const uint32_t c = sh.cp[(E - seg_start) / CP_BITS - 1u][k];
-        if (seg_start + (c >> 16) == E) { sh.rexit[k] = spec_exit; sh.rcnt[k] = spec_cnt - (c & 0xFFFFu); return true; }
-    }
-    return false;
-}
-
-// CTA-COLLECTIVE (every warp, converged): the lanes drain the job pool.  g0 = global segment of slot 0.
-__device__ __forceinline__ void run_merge_jobs(SyncShared& sh, const uint8_t* __restrict__ payload,
-                                               const StreamDesc* __restrict__ streams,
-                                               const uint32_t* __restrict__ seg_stream, uint32_t g0) {
-    const uint32_t njobs = sh.njobs;
+// Resolve slot t for entry E.  WARP-COLLECTIVE (lanes with nothing to resolve pass need = false): the
+// symbol loop is uniform, lanes without a merge to do are parked.  s0 = f position of the super's first bit.
+__device__ __forceinline__ void resolve_super(SyncShared& sh, const uint8_t* base, uint32_t E, uint32_t s0, uint32_t ftotal,
+                                              int t, bool need) {
+    const uint32_t fstop_eos = eos_stop(ftotal);
+    uint32_t jb = 1;                                   // next segment boundary to resolve
+    uint32_t cnt = 0, inext = 0, next_stop = NO_WORK;
     Parser ps;
     ps.init_parked();
-    uint32_t jt = 0, seg_start = 0, ftotal = 0, fstop_eos = 0, cnt = 0, next_cp = 0, next_stop = NO_WORK;
-    auto grab = [&]() {
-        const uint32_t k = atomicAdd(&sh.next, 1u);
-        if (k < njobs) {
-            jt = sh.job[k];
-            const SegCtx c = seg_ctx(payload, streams, seg_stream, g0 + jt);
-            const uint32_t E = sh.E[jt];
-            seg_start = c.seg_start; ftotal = c.ftotal; fstop_eos = eos_stop(c.ftotal);
-            ps.start(c.base, E, ftotal);
-            cnt = 0;
-            next_cp = seg_start + ((E - seg_start) / CP_BITS + 1u) * CP_BITS;   // first boundary after E (E >= seg_start)
-            next_stop = min(next_cp, fstop_eos);
-        } else {
-            ps.park();
-            next_stop = NO_WORK;
+    // fill boundaries jb.. from checkpoint i (merged there with `cnt` blocks counted from E so far)
+    auto finish_from = [&](uint32_t i, uint32_t cnt_here) {
+        const uint32_t ci = sh.cp[i][t];
+        for (; jb <= (uint32_t)SUPER; jb++) {
+            const uint32_t c = sh.cp[ck_of_seg(jb)][t];
+            sh.tpos[jb][t] = s0 + (c >> 16);
+            sh.tcnt[jb][t] = cnt_here + (c & 0xFFFFu) - (ci & 0xFFFFu);
         }
     };
-    grab();
+    auto finish_at = [&](uint32_t pos, uint32_t cnt_here) {      // no merge: every remaining boundary sees `pos`
+        for (; jb <= (uint32_t)SUPER; jb++) { sh.tpos[jb][t] = pos; sh.tcnt[jb][t] = cnt_here; }
+    };
+    if (need) {
+        sh.tpos[0][t] = E;
+        sh.tcnt[0][t] = 0;
+        if (E >= s0 + SUPER_BITS || E >= fstop_eos) finish_at(E, 0);                       // owns nothing
+        else if (E == s0) {                                                                 // speculation was right
+            for (; jb <= (uint32_t)SUPER; jb++) {
+                const uint32_t c = sh.cp[ck_of_seg(jb)][t];
+                sh.tpos[jb][t] = s0 + (c >> 16); sh.tcnt[jb][t] = c & 0xFFFFu;
+            }
+        } else {
+            // segment boundaries already behind E (a block that spans them): they see E itself
+            for (; jb < (uint32_t)SUPER && E >= s0 + jb * SEG_BITS; jb++) { sh.tpos[jb][t] = E; sh.tcnt[jb][t] = 0; }
+            bool merged = false;
+            if (E >= s0 + CP_BITS) {                                                        // E itself may be a recorded block start
+                const uint32_t i = ck_last(E - s0);
+                if (s0 + (sh.cp[i][t] >> 16) == E) { finish_from(i, 0); merged = true; }
+                inext = i + 1u;
+            }
+            if (!merged) {
+                ps.start(base, E, ftotal);
+                next_stop = min(s0 + ck_bnd(inext), fstop_eos);
+            }
+        }
+    }
     while (__any_sync(FULL_MASK, next_stop != NO_WORK)) {
         Parser::Sym y;
         const bool end = ps.step<false>(ftotal, y);
@@ -162,76 +180,61 @@ __device__ __forceinline__ void run_merge_jobs(SyncShared& sh, const uint8_t* __
         if (end && ps.fpos >= next_stop) {               // rare: first block start past a boundary / end of stream
             const uint32_t pos = ps.fpos;
             bool done = false;
-            uint32_t exit_pos = pos;
-            if (pos >= next_cp) {
-                const uint32_t j = min((uint32_t)NCP, (pos - seg_start) / CP_BITS) - 1u;
-                const uint32_t c = sh.cp[j][jt];
-                if (seg_start + (c >> 16) == pos) {      // merged with the speculative trajectory
-                    const uint32_t last = sh.cp[NCP - 1][jt];
-                    cnt += (last & 0xFFFFu) - (c & 0xFFFFu);
-                    exit_pos = seg_start + (last >> 16);
+            if (pos >= s0 + ck_bnd(inext)) {
+                const uint32_t i = ck_last(pos - s0);
+                // segment boundaries passed on the way (all but possibly the last are strictly before pos's checkpoint)
+                for (; jb <= (uint32_t)SUPER && ck_of_seg(jb) < i; jb++) { sh.tpos[jb][t] = pos; sh.tcnt[jb][t] = cnt; }
+                if (s0 + (sh.cp[i][t] >> 16) == pos) {   // merged with the speculative trajectory
+                    finish_from(i, cnt);
                     done = true;
-                }
-                next_cp = seg_start + (j + 2u) * CP_BITS;
+                } else if (jb <= (uint32_t)SUPER && ck_of_seg(jb) == i) { sh.tpos[jb][t] = pos; sh.tcnt[jb][t] = cnt; jb++; }
+                inext = i + 1u;
+                if (!done && inext == (uint32_t)NCK) done = true;      // past the super's end without a merge
             }
-            if (!done && (pos >= seg_start + SEG_BITS || pos >= fstop_eos)) done = true;
-            if (done) { sh.rexit[jt] = exit_pos; sh.rcnt[jt] = cnt; grab(); }
-            else next_stop = min(next_cp, fstop_eos);
+            if (!done && pos >= fstop_eos) { finish_at(pos, cnt); done = true; }
+            if (done) { ps.park(); next_stop = NO_WORK; }
+            else next_stop = min(s0 + ck_bnd(inext), fstop_eos);
         }
     }
 }
 
-// Segments [seg_lo, seg_hi) of the plan.
+// Supers [sup_lo, sup_hi) of the plan.
 __global__ void __launch_bounds__(ENT_TPB)
 k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
-               const uint32_t* __restrict__ seg_stream, uint32_t seg_lo, uint32_t seg_hi,
+               const uint32_t* __restrict__ seg_stream, uint32_t sup_lo, uint32_t sup_hi,
                uint32_t* __restrict__ seg_entry, uint32_t* __restrict__ seg_exit, uint32_t* __restrict__ seg_cnt) {
     __shared__ SyncShared sh;
     const int t = threadIdx.x;
-    // slot k <-> global segment g0 + k; slot 0 (the halo) does not exist for the first CTA
-    const uint32_t g0 = seg_lo + blockIdx.x * SYNC_OWN - 1u;
-    const uint32_t k_lo = blockIdx.x == 0 ? 1u : 0u;
-    const uint32_t k_hi = min((uint32_t)SYNC_SLOTS, seg_hi - g0);       // slots [k_lo, k_hi) exist
-    if (t == 0) { sh.njobs = 0; sh.next = ENT_TPB; }
-    __syncthreads();
+    const uint32_t u = sup_lo + blockIdx.x * SYNC_OWN + (uint32_t)t - 1u;        // slot t <-> super u; slot 0 = halo
+    const bool valid = (blockIdx.x != 0 || t != 0) && u < sup_hi;
+    SegCtx c{};
+    if (valid) c = seg_ctx(payload, streams, seg_stream, u * SUPER);
+    const uint32_t ftotal = c.ftotal, fstop_eos = eos_stop(c.ftotal), s0 = c.seg_start;
 
-    // ---- phase A: speculative parse of every slot from the segment's first bit ----------------------------
+    // ---- phase A: speculative parse of the super from its first bit ---------------------------------------
     {
         Parser ps;
         ps.init_parked();
-        uint32_t slot = 0, seg_start = 0, ftotal = 0, fstop_eos = 0, cnt = 0, j = 0, next_cp = 0, next_stop = NO_WORK;
-        auto grab = [&](uint32_t k) {
-            for (;; k = atomicAdd(&sh.next, 1u)) {
-                if (k >= k_hi) { ps.park(); next_stop = NO_WORK; return; }
-                if (k < k_lo) continue;
-                const SegCtx c = seg_ctx(payload, streams, seg_stream, g0 + k);
-                slot = k; seg_start = c.seg_start; ftotal = c.ftotal; fstop_eos = eos_stop(c.ftotal);
-                if (seg_start >= fstop_eos) {            // segment in the stream's trailing pad: nothing to parse
+        uint32_t cnt = 0, j = 0, next_stop = NO_WORK;
+        if (valid && s0 < fstop_eos) { ps.start(c.base, s0, ftotal); next_stop = min(s0 + ck_bnd(0), fstop_eos); }
+        else if (valid) {                                // super in the stream's trailing pad: nothing to parse
 #pragma unroll
-                    for (int i = 0; i < NCP; i++) sh.cp[i][k] = 0u;
-                    continue;
-                }
-                ps.start(c.base, seg_start, ftotal);
-                cnt = 0; j = 0;
-                next_cp = seg_start + CP_BITS;
-                next_stop = min(next_cp, fstop_eos);
-                return;
-            }
-        };
-        grab((uint32_t)t);
+            for (int i = 0; i < NCK; i++) sh.cp[i][t] = 0u;
+        }
         while (__any_sync(FULL_MASK, next_stop != NO_WORK)) {
             Parser::Sym y;
             const bool end = ps.step<false>(ftotal, y);
             cnt += end ? 1u : 0u;
             if (end && ps.fpos >= next_stop) {           // rare: a checkpoint boundary or the end of the stream passed
                 const uint32_t pos = ps.fpos;
-                const uint32_t rec = ((pos - seg_start) << 16) | cnt;
-                while (j < (uint32_t)NCP && pos >= next_cp) { sh.cp[j][slot] = rec; j++; next_cp += CP_BITS; }
-                if (j == (uint32_t)NCP || pos >= fstop_eos) {   // end of stream: no further block can start
-                    for (; j < (uint32_t)NCP; j++) sh.cp[j][slot] = rec;
-                    grab(atomicAdd(&sh.next, 1u));
+                const uint32_t rec = ((pos - s0) << 16) | cnt;
+                while (j < (uint32_t)NCK && pos >= s0 + ck_bnd(j)) { sh.cp[j][t] = rec; j++; }
+                if (j == (uint32_t)NCK || pos >= fstop_eos) {   // end of stream: no further block can start
+                    for (; j < (uint32_t)NCK; j++) sh.cp[j][t] = rec;
+                    ps.park();
+                    next_stop = NO_WORK;
                 } else {
-                    next_stop = min(next_cp, fstop_eos);
+                    next_stop = min(s0 + ck_bnd(j), fstop_eos);
                 }
             }
         }
@@ -239,54 +242,28 @@ k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
     __syncthreads();
 
     // ---- phase B, round 1: entry = predecessor's speculative exit -------------------------------------------
-    if (t == 0) sh.next = 0;
-#pragma unroll
-    for (int i = 0; i < SYNC_PER_THREAD; i++) {
-        const uint32_t k = (uint32_t)t + (uint32_t)i * ENT_TPB;
-        if (k < k_lo || k >= k_hi) continue;
-        const SegCtx c = seg_ctx(payload, streams, seg_stream, g0 + k);
-        if (k == 0) {                                    // the halo keeps its speculative exit
-            sh.E[0] = c.seg_start; sh.rexit[0] = c.seg_start + (sh.cp[NCP - 1][0] >> 16); sh.rcnt[0] = 0;
-            continue;
-        }
-        const uint32_t E = c.seg ? c.seg_start - SEG_BITS + (sh.cp[NCP - 1][k - 1] >> 16) : c.bias;
-        if (!resolve_trivial(sh, k, E, c.seg_start, eos_stop(c.ftotal))) sh.job[atomicAdd(&sh.njobs, 1u)] = k;
-    }
-    __syncthreads();
-    run_merge_jobs(sh, payload, streams, seg_stream, g0);
+    const bool own = valid && t >= 1;
+    const bool has_pred = own && c.seg != 0;             // same stream as slot t-1 (streams are SUPER-aligned)
+    uint32_t E = has_pred ? s0 - SUPER_BITS + (sh.cp[NCK - 1][t - 1] >> 16) : c.bias;
+    resolve_super(sh, c.base, E, s0, ftotal, t, own);
+    if (valid && t == 0) sh.tpos[SUPER][0] = s0 + (sh.cp[NCK - 1][0] >> 16);     // the halo keeps its speculative exit
     __syncthreads();
     // ---- round 2: re-merge where the predecessor's resolved exit differs from its speculative one ----------
-    uint32_t E2[SYNC_PER_THREAD];
-#pragma unroll
-    for (int i = 0; i < SYNC_PER_THREAD; i++) {
-        const uint32_t k = (uint32_t)t + (uint32_t)i * ENT_TPB;
-        E2[i] = NO_WORK;
-        if (k < max(k_lo, 1u) || k >= k_hi) continue;
-        const SegCtx c = seg_ctx(payload, streams, seg_stream, g0 + k);
-        if (c.seg && sh.rexit[k - 1] != sh.E[k]) E2[i] = sh.rexit[k - 1];
+    const uint32_t E2 = has_pred ? sh.tpos[SUPER][t - 1] : E;
+    __syncthreads();                                      // every tpos[SUPER][t-1] read before round 2 overwrites any
+    const bool redo = own && E2 != E;
+    if (__syncthreads_or(redo)) {
+        if (redo) E = E2;
+        resolve_super(sh, c.base, E, s0, ftotal, t, redo);
     }
-    __syncthreads();                                      // every rexit[k-1] read before round 2 overwrites any
-    if (t == 0) { sh.njobs = 0; sh.next = 0; }
-    __syncthreads();
+    if (own) {
 #pragma unroll
-    for (int i = 0; i < SYNC_PER_THREAD; i++) {
-        const uint32_t k = (uint32_t)t + (uint32_t)i * ENT_TPB;
-        if (E2[i] == NO_WORK) continue;
-        const SegCtx c = seg_ctx(payload, streams, seg_stream, g0 + k);
-        if (!resolve_trivial(sh, k, E2[i], c.seg_start, eos_stop(c.ftotal))) sh.job[atomicAdd(&sh.njobs, 1u)] = k;
-    }
-    __syncthreads();
-    if (sh.njobs) run_merge_jobs(sh, payload, streams, seg_stream, g0);
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < SYNC_PER_THREAD; i++) {
-        const uint32_t k = (uint32_t)t + (uint32_t)i * ENT_TPB;
-        if (k < 1u || k >= k_hi) continue;
-        const uint32_t g = g0 + k;
-        const uint32_t bias = stream_bias(payload + streams[__ldg(seg_stream + g)].byte_off);
-        seg_entry[g] = sh.E[k] - bias;
-        seg_exit[g] = sh.rexit[k] - bias;
-        seg_cnt[g] = sh.rcnt[k];
+        for (int j = 0; j < SUPER; j++) {
+            const uint32_t g = u * SUPER + j;
+            seg_entry[g] = sh.tpos[j][t] - c.bias;
+            seg_exit[g] = sh.tpos[j + 1][t] - c.bias;
+            seg_cnt[g] = sh.tcnt[j + 1][t] - sh.tcnt[j][t];
+        }
     }
 }
 
@@ -500,7 +477,7 @@ __global__ void __launch_bounds__(128)
 k_seg_stream(const StreamDesc* __restrict__ streams, uint32_t n_streams, uint32_t* __restrict__ seg_stream) {
     const uint32_t s = blockIdx.x * 4u + (threadIdx.x >> 5);
     if (s >= n_streams) return;
-    const uint32_t base = streams[s].seg_base, n = streams[s].nseg;
+    const uint32_t base = streams[s].seg_base, n = (streams[s].nseg + SUPER - 1) / SUPER * SUPER;   // incl. the padding segments
     for (uint32_t i = threadIdx.x & 31; i < n; i += 32) seg_stream[base + i] = s;
 }
 cudaError_t launch_seg_stream(const StreamDesc* d_streams, uint32_t n_streams, uint32_t* d_seg_stream, cudaStream_t s) {
@@ -511,9 +488,10 @@ cudaError_t launch_seg_stream(const StreamDesc* d_streams, uint32_t n_streams, u
 
 cudaError_t launch_entropy_sync(const EntropyJob& j, cudaStream_t s) {
     if (j.seg_hi <= j.seg_lo) return cudaSuccess;
-    const uint32_t n = j.seg_hi - j.seg_lo;
-    k_entropy_sync<<<(n + SYNC_OWN - 1) / SYNC_OWN, ENT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo,
-                                                                    j.seg_hi, j.d_seg_entry, j.d_seg_exit, j.d_seg_cnt);
+    const uint32_t sup_lo = j.seg_lo / SUPER, sup_hi = j.seg_hi / SUPER;       // chunk ranges are SUPER-aligned (build_plan)
+    const uint32_t n = sup_hi - sup_lo;
+    k_entropy_sync<<<(n + SYNC_OWN - 1) / SYNC_OWN, ENT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, sup_lo, sup_hi,
+                                                                    j.d_seg_entry, j.d_seg_exit, j.d_seg_cnt);
     return cudaGetLastError();
 }
 cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s) {

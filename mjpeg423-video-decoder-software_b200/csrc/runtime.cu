@@ -98,7 +98,7 @@ int build_plan(const MpgIndex& idx, uint32_t first, uint32_t n, Plan& plan) {
             sd.prev_base = r.type ? sd.block_base - 3 * plan.nb : sd.block_base;   // frame 0 is an I frame
             sd.quant_id = p ? 1 : 0; sd.ptype = (uint16_t)r.type;
             plan.streams.push_back(sd);
-            seg_base += sd.nseg; so += lens[p];
+            seg_base += (sd.nseg + SUPER - 1) / SUPER * SUPER; so += lens[p];     // padded: see SUPER (common.cuh)
             plan.stream_bytes += lens[p];
         }
     }
