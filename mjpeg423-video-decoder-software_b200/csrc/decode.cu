@@ -329,17 +329,20 @@ k_decode_fused(const uint2* __restrict__ blk_info,
             }
             // ---- pass 2: rows (idct.c:116-180) ------------------------------------------------------------------
 #pragma unroll 1
-            for (int r = 0; r < 8; r++) {
-                const uint2* row = reinterpret_cast<const uint2*>(s_ws + (r >> 1) * FUSED_TPB + t) + (r & 1);
-                const uint2 a = row[0], bq = row[4 * FUSED_TPB * 2];
-                int o[8];
+            for (int r = 0; r < 8; r += 2) {                          // two rows per iteration: one LDS.128 per column pair
+                const uint4* g = s_ws + (r >> 1) * FUSED_TPB + t;      // and two independent butterflies in flight
+                const uint4 a = g[0], bq = g[4 * FUSED_TPB];
+                int o0[8], o1[8];
                 if (high_half) {
-                    const uint2 cq = row[8 * FUSED_TPB * 2], dq = row[12 * FUSED_TPB * 2];
-                    idct8<18>((int)a.x, (int)a.y, (int)bq.x, (int)bq.y, (int)cq.x, (int)cq.y, (int)dq.x, (int)dq.y, o);
+                    const uint4 cq = g[8 * FUSED_TPB], dq = g[12 * FUSED_TPB];
+                    idct8<18>((int)a.x, (int)a.y, (int)bq.x, (int)bq.y, (int)cq.x, (int)cq.y, (int)dq.x, (int)dq.y, o0);
+                    idct8<18>((int)a.z, (int)a.w, (int)bq.z, (int)bq.w, (int)cq.z, (int)cq.w, (int)dq.z, (int)dq.w, o1);
                 } else {
-                    idct8<18>((int)a.x, (int)a.y, (int)bq.x, (int)bq.y, 0, 0, 0, 0, o);
+                    idct8<18>((int)a.x, (int)a.y, (int)bq.x, (int)bq.y, 0, 0, 0, 0, o0);
+                    idct8<18>((int)a.z, (int)a.w, (int)bq.z, (int)bq.w, 0, 0, 0, 0, o1);
                 }
-                emit(r, pack4_sat_u8(o[0], o[1], o[2], o[3]), pack4_sat_u8(o[4], o[5], o[6], o[7]));
+                emit(r, pack4_sat_u8(o0[0], o0[1], o0[2], o0[3]), pack4_sat_u8(o0[4], o0[5], o0[6], o0[7]));
+                emit(r + 1, pack4_sat_u8(o1[0], o1[1], o1[2], o1[3]), pack4_sat_u8(o1[4], o1[5], o1[6], o1[7]));
             }
         }
     }
