@@ -354,9 +354,13 @@ k_entropy_chain(const uint8_t* __restrict__ payload, const StreamDesc* __restric
 // After this pass no kernel touches the bitstream again: the block-parallel decode kernels (decode.cu)
 // read the lists with independent, look-ahead loads instead of a bit-serial dependent chain.
 // ------------------------------------------------------------------------------------------------
-constexpr int INDEX_SLOTS = 512;     // segments per CTA
+// Small CTAs, one segment per lane: measured best (3.75 ms / 2000 frames at 1080p; pools of 2 / 4 / 8 segments per
+// lane pulled from the CTA-wide counter: 4.0 / 4.45 / 4.8 ms) -- the hardware CTA scheduler balances many short CTAs
+// better than lanes balance inside a long-lived one.  The pull loop below stays general (INDEX_SLOTS >= INDEX_TPB).
+constexpr int INDEX_TPB = 64;
+constexpr int INDEX_SLOTS = 64;      // segments per CTA
 
-__global__ void __launch_bounds__(ENT_TPB, 8)
+__global__ void __launch_bounds__(INDEX_TPB, 16)
 k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
                 const uint32_t* __restrict__ seg_stream, uint32_t seg_lo, uint32_t seg_hi,
                 const uint32_t* __restrict__ seg_entry, const uint32_t* __restrict__ seg_cnt,
@@ -366,7 +370,7 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
     const int t = threadIdx.x;
     const uint32_t g0 = seg_lo + blockIdx.x * INDEX_SLOTS;
     const uint32_t k_hi = min((uint32_t)INDEX_SLOTS, seg_hi - g0);
-    if (t == 0) s_next = ENT_TPB;
+    if (t == 0) s_next = INDEX_TPB;
     __syncthreads();
 
     Parser ps;
@@ -504,7 +508,7 @@ cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s) {
 cudaError_t launch_entropy_index(const EntropyJob& j, cudaStream_t s) {
     if (j.seg_hi <= j.seg_lo) return cudaSuccess;
     const uint32_t n = j.seg_hi - j.seg_lo;
-    k_entropy_index<<<(n + INDEX_SLOTS - 1) / INDEX_SLOTS, ENT_TPB, 0, s>>>(
+    k_entropy_index<<<(n + INDEX_SLOTS - 1) / INDEX_SLOTS, INDEX_TPB, 0, s>>>(
         j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry, j.d_seg_cnt, j.d_seg_first, j.d_seg_dc,
         j.d_blk_info, j.d_sym, j.sym_seg0, j.d_fixups + 1);
     cudaError_t e = cudaGetLastError();
