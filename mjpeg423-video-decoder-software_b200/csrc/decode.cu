@@ -296,7 +296,7 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                     // Flat Cb and Cr blocks: the chroma terms are per-block constants.
                     if (live) {
                         const FlatChroma fc(s_stash[16 * FUSED_TPB + t] & 255u, s8);
-#pragma unroll 1
+#pragma unroll 2
                         for (int r = 0; r < 8; r++)
                             fc.row_store(s_stash[(2 * r) * FUSED_TPB + t], s_stash[(2 * r + 1) * FUSED_TPB + t],
                                          dst + (size_t)r * W * 4);
