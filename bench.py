@@ -171,6 +171,17 @@ def procedural_frames(W: int, H: int, n: int, uniq: int, amp: int) -> np.ndarray
     return base[np.arange(n) % uniq]
 
 
+def _encode_worker(job):
+    """One host process of the encoder's reference arm: encode a `per`-frame clip `reps` times."""
+    W, H, per, amp, max_i, reps = job
+    from oracle import oracle
+    chk = oracle.best()
+    clip = procedural_frames(W, H, per, per, amp)
+    for _ in range(reps):
+        chk.encode_mpg(clip, max_i)
+    return reps
+
+
 def encoder_bench(args, rank: int, world: int, local_rank: int):
     """encoded frames/s of mjpeg423_b200_encode_frames (frames -> complete .mpg in host memory).
     `value`: frames already resident in HBM; `e2e`: pinned host frames in.  --impl reference: the reference's own
@@ -183,26 +194,25 @@ def encoder_bench(args, rank: int, world: int, local_rank: int):
     if args.impl == "reference":
         if rank != 0:
             return
-        import threading
+        from concurrent.futures import ProcessPoolExecutor
         from oracle import oracle
         chk = oracle.best()
         per = 4 if H >= 1080 else 16
-        clip = procedural_frames(W, H, per, per, amp)
-        def work():
-            chk.encode_mpg(clip, max_i)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            th = [threading.Thread(target=work) for _ in range(cores)]
-            [t.start() for t in th]
-            [t.join() for t in th]
-        dt = time.perf_counter() - t0
+        # one PROCESS per core: the reference's lossless_encode keeps its bit buffer in file-scope globals
+        # (LIB/encoder/lossless_encode.c:17-19) and is not thread-safe
+        with ProcessPoolExecutor(max_workers=cores) as pool:
+            list(pool.map(_encode_worker, [(W, H, per, amp, max_i, 0)] * cores))        # start-up + warm-up
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                list(pool.map(_encode_worker, [(W, H, per, amp, max_i, 1)] * cores))
+            dt = time.perf_counter() - t0
         fps = per * cores * args.steps / dt
         print(json.dumps({"impl": "reference", "metric": "encoded frames/sec", "value": fps, "unit": "frames/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32",
                           "data": "synthetic", "config": {"workload": args.workload, "width": W, "height": H, "max_I_interval": max_i},
                           "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": chk.kind,
-                                           "sample": f"{cores} threads x {per}-frame clip per step"},
+                                           "sample": f"{cores} processes x {per}-frame clip per step"},
                           "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0}), flush=True)
         return
