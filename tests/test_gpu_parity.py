@@ -393,3 +393,23 @@ def test_error_paths(dec):
     except RuntimeError as e:
         assert "blocks" in str(e)
     assert np.array_equal(dec.decode_frames(mpg, 0, 0).shape, (0, 48, 64, 4))   # empty range
+
+
+def test_garbage_streams_are_survived(checker):
+    """Non-conforming input (random bytes, all-ZRL, all-ones, truncated): the reference has undefined behaviour there
+    (it indexes zigzag_table unchecked, LIB/decoder/lossless_decode.c:101-125), so nothing is compared with it --
+    the library must neither fault nor hang, must be deterministic, and must decode a good stream afterwards."""
+    rng = np.random.default_rng(99)
+    cases = [rng.integers(0, 256, size=n, dtype=np.uint8).tobytes() for n in (1, 7, 600, 5000, 70000)]
+    cases += [b"\xF0" * 9000, b"\xFF" * 9000, b"\x00" * 3, b"\x0F" * 4000]
+    for nb in (1, 50, 3000):
+        for raw in cases:
+            a = mjpeg423_b200.lossless_decode(nb, raw, None, api.YQUANT, 0)
+            b = mjpeg423_b200.lossless_decode(nb, raw, None, api.YQUANT, 0)
+            assert a.shape == (nb, 8, 8) and np.array_equal(a, b)
+    lv = _random_levels(rng, 200, 0.1, 30, 100)
+    wire = lv.copy()
+    wire[1:, 0] = lv[1:, 0] - lv[:-1, 0]
+    stream = _encode_levels(wire)
+    assert np.array_equal(mjpeg423_b200.lossless_decode(200, stream, None, api.YQUANT, 0),
+                          checker.lossless_decode(200, stream, api.YQUANT, 0))
