@@ -54,7 +54,9 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons of one GPU, sampled every 50 ms.  The sampler is started EARLY (nvidia-smi
+    needs about a second to enumerate an 8-GPU box) and reads its lines with their arrival time; begin()/end() mark the
+    timed region and stop() reports the samples that arrived inside it."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -62,27 +64,47 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
+        self.lines = []                 # (arrival time, text)
+        self.t_begin = self.t_end = None
 
     def start(self):
+        import threading
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(self.gpu)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
         except Exception:
             self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.lines.append((time.perf_counter(), line))
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
+
+    def end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.t_end is None:
+            self.end()
+        time.sleep(0.06)                # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-            out = ""
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        inside = [l for t, l in self.lines if t0 <= t <= self.t_end + 0.06]
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.splitlines():
+        for line in inside:
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 8:
                 continue
@@ -93,10 +115,7 @@ class ClockSampler:
             for nm, v in zip(names, parts[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        # the first samples may predate the load; take the median of the upper half
-        sm_sorted = sorted(sm)
-        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
-        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(smax) if smax else None,
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
@@ -225,6 +244,8 @@ def encoder_bench(args, rank: int, world: int, local_rank: int):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     fr = procedural_frames(W, H, frames, uniq, amp)
     dec = mjpeg423_b200.Decoder(local_rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     d = dec.device_alloc(fr.nbytes)
     dec.to_device(d, fr)
     mpg = dec.encode_frames(None, max_i, d_frames=d, shape=(frames, H, W))
@@ -245,9 +266,8 @@ def encoder_bench(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
     for _ in range(args.warmup):
         dec.encode_frames(None, max_i, d_frames=d, shape=(frames, H, W))
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.begin()
     ev_ms, launches = 0.0, 0
     for _ in range(args.steps):
         dec.encode_frames(None, max_i, d_frames=d, shape=(frames, H, W))
@@ -255,6 +275,7 @@ def encoder_bench(args, rank: int, world: int, local_rank: int):
         ev_ms += st["total_ms"]
         launches += st["kernel_launches"]
     barrier()
+    sampler.end()
     clocks = sampler.stop()
     pin = dec.pinned(fr.nbytes)
     pin.array[:] = fr.reshape(-1)
@@ -352,6 +373,8 @@ def main():
     P = W * H
 
     dec = mjpeg423_b200.Decoder(local_rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                          # early: nvidia-smi takes a while to deliver its first line
     if q is not None:
         dec.set_quant(q, q)
     info = dec.upload(mpg)
@@ -381,9 +404,8 @@ def main():
     # ---- device-resident throughput -------------------------------------------------------------------------
     for _ in range(args.warmup):
         dec.decode_resident(d_out)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.begin()
     ev_ms, launches = 0.0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -393,6 +415,7 @@ def main():
         launches += st["kernel_launches"]
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
+    sampler.end()
     clocks = sampler.stop()
     payload_bytes = st["payload_bytes"]
 
