@@ -55,9 +55,11 @@ struct StreamDesc {
 //   DC symbol  input_DC  LIB/decoder/lossless_decode.c:210-224  (4-bit size + amplitude)
 //   AC symbol  input_AC  :227-246 (4-bit run, 4-bit size, amplitude); size 0: run 15 = ZRL else END
 //   block loop :101-133; `index` is uint8_t there and wraps, so it does here.
-// A block is also ended when it reaches `flim` = min(block start + RUNAWAY_BITS, end of stream): memory
-// safety and termination on non-conforming input and on speculative garbage (conforming blocks are
-// <= 1212 bits).
+// A block is also ended when it reaches `flim` = min(end of the pass's job + RUNAWAY_BITS, end of stream):
+// memory safety and termination on non-conforming input and on speculative garbage (a block made of ZRL symbols
+// never ends by itself; conforming blocks are <= 1212 bits, SURVEY.md A.6, and never get near the limit).  The
+// limit is a constant of the job, not of the block: keeping it per block cost two ALU-pipe instructions per symbol
+// in passes that are bound by that pipe.
 //
 // Bit window (replaces update_buffer / INPUT_BITS, lossless_decode.c:139-162,207; only the number of
 // consumed bits is observable, so the mechanics are free): two consecutive big-endian 32-bit words
@@ -77,20 +79,21 @@ struct Parser {
     const uint32_t* wp;    // next aligned word to fetch
     uint32_t w0, w1, w2;   // current word, look-ahead word, word in flight; MSB first
     uint32_t fpos;         // f position of the next symbol
-    uint32_t flim;         // the current block is ended at or after this f position
+    uint32_t flim;         // a block is ended at or after this f position (see above)
     uint32_t idx;          // zig-zag index of the next AC coefficient
     uint32_t nh;           // minus the header length of the next symbol: -4 = DC (a block start), -8 = AC
     uint32_t rmask;        // 32 while live; 0 = PARKED: the window is never refilled again (see park())
 
-    // fbits = f position to start at (a block start), ftotal = f position of the end of the stream.
-    __device__ __forceinline__ void start(const uint8_t* base, uint32_t fbits, uint32_t ftotal) {
+    // fbits = f position to start at (a block start), job_end = f position where the caller's job ends (it stops at
+    // the first block start at or after it), ftotal = f position of the end of the stream.
+    __device__ __forceinline__ void start(const uint8_t* base, uint32_t fbits, uint32_t job_end, uint32_t ftotal) {
         const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)3) + (fbits >> 5);
         w0 = __byte_perm(__ldg(w), 0, 0x0123);
         w1 = __byte_perm(__ldg(w + 1), 0, 0x0123);
         w2 = __ldg(w + 2);                               // kept raw: byte-swapped when it moves into w1
         wp = w + 3;
         fpos = fbits;
-        flim = min(fbits + RUNAWAY_BITS, ftotal);
+        flim = min(job_end + RUNAWAY_BITS, ftotal);
         idx = 1;
         nh = (uint32_t)-4;
         rmask = 32u;
@@ -115,7 +118,7 @@ struct Parser {
     // Consume one symbol.  Returns true when it ended the block (the parser is then positioned on the
     // next block's DC symbol).
     template <bool WANT_E>
-    __device__ __forceinline__ bool step(uint32_t ftotal, Sym& sym) {
+    __device__ __forceinline__ bool step(Sym& sym) {
         const uint32_t t = __funnelshift_l(w1, w0, fpos);               // next 32 stream bits
         const bool dc = nh == (uint32_t)-4;
         const uint32_t rs = __funnelshift_r(t, 0u, nh);                 // t >> (32 - header bits): the 4 / 8 header bits
@@ -142,7 +145,6 @@ struct Parser {
         const bool end = (!szd && run != 15u) || (coded && at >= 63u) || fnew >= flim;   // END / coefficient 63 / guard
         idx = end ? 1u : at + (coded ? 1u : 0u);
         nh = end ? (uint32_t)-4 : (uint32_t)-8;
-        if (end) flim = min(fnew + RUNAWAY_BITS, ftotal);
         fpos = fnew;
         sym.dc = dc;
         sym.coded = coded;

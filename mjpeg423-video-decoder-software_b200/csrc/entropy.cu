@@ -56,10 +56,10 @@ __device__ __forceinline__ uint32_t parse_segment(const uint8_t* base, uint32_t 
     const uint32_t stop = min(seg_end, eos_stop(ftotal));
     if (pos < stop) {
         Parser ps;
-        ps.start(base, entry, ftotal);
+        ps.start(base, entry, seg_end, ftotal);
         for (;;) {
             Parser::Sym y;
-            if (ps.step<false>(ftotal, y)) {
+            if (ps.step<false>(y)) {
                 cnt++;
                 if (ps.fpos >= stop) break;
             }
@@ -168,14 +168,14 @@ __device__ __forceinline__ void resolve_super(SyncShared& sh, const uint8_t* bas
                 inext = i + 1u;
             }
             if (!merged) {
-                ps.start(base, E, ftotal);
+                ps.start(base, E, s0 + SUPER_BITS, ftotal);
                 next_stop = min(s0 + ck_bnd(inext), fstop_eos);
             }
         }
     }
     while (__any_sync(FULL_MASK, next_stop != NO_WORK)) {
         Parser::Sym y;
-        const bool end = ps.step<false>(ftotal, y);
+        const bool end = ps.step<false>(y);
         cnt += end ? 1u : 0u;
         if (end && ps.fpos >= next_stop) {               // rare: first block start past a boundary / end of stream
             const uint32_t pos = ps.fpos;
@@ -216,14 +216,14 @@ k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
         Parser ps;
         ps.init_parked();
         uint32_t cnt = 0, j = 0, next_stop = NO_WORK;
-        if (valid && s0 < fstop_eos) { ps.start(c.base, s0, ftotal); next_stop = min(s0 + ck_bnd(0), fstop_eos); }
+        if (valid && s0 < fstop_eos) { ps.start(c.base, s0, s0 + SUPER_BITS, ftotal); next_stop = min(s0 + ck_bnd(0), fstop_eos); }
         else if (valid) {                                // super in the stream's trailing pad: nothing to parse
 #pragma unroll
             for (int i = 0; i < NCK; i++) sh.cp[i][t] = 0u;
         }
         while (__any_sync(FULL_MASK, next_stop != NO_WORK)) {
             Parser::Sym y;
-            const bool end = ps.step<false>(ftotal, y);
+            const bool end = ps.step<false>(y);
             cnt += end ? 1u : 0u;
             if (end && ps.fpos >= next_stop) {           // rare: a checkpoint boundary or the end of the stream passed
                 const uint32_t pos = ps.fpos;
@@ -375,7 +375,7 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
 
     Parser ps;
     ps.init_parked();
-    uint32_t g = 0, ftotal = 0, cnt = 0, k = 0, o = 0, o_blk = 0, o_end = 0, written = 0, tag = 0;
+    uint32_t g = 0, cnt = 0, k = 0, o = 0, o_blk = 0, o_end = 0, written = 0, tag = 0;
     uint2* bi = nullptr;
     int cur = 0;
     bool pframe = false;
@@ -395,8 +395,7 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
             if (c.seg + 1u == sd->nseg)
                 for (uint32_t b = first + cnt; b < nb; b++) blk_info[sd->block_base + b] = make_uint2(BLK_NO_SEG, 0);
             if (cnt == 0) { seg_dc[g] = 0u; continue; }
-            ftotal = c.ftotal;
-            ps.start(c.base, seg_entry[g] + c.bias, ftotal);
+            ps.start(c.base, seg_entry[g] + c.bias, c.seg_start + SEG_BITS, c.ftotal);
             bi = blk_info + sd->block_base + first;
             tag = (first & 31u) << 6;                    // (index of the block being parsed & 31) << 6
             o = o_blk = (g - sym_seg0) * SYM_STRIDE;     // chunk-relative entry index
@@ -409,7 +408,7 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
     grab((uint32_t)t);
     while (__any_sync(FULL_MASK, cnt != 0u)) {
         Parser::Sym y;
-        const bool end = ps.step<true>(ftotal, y);
+        const bool end = ps.step<true>(y);
         if (y.dc) { cur = pframe ? y.e : cur + y.e; o_blk = o; }
         if (y.coded && y.at < 64u) {                     // (a parked lane never sees a coded symbol)
 #pragma unroll
