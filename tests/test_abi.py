@@ -91,3 +91,20 @@ def test_frame_hash_host_is_position_sensitive():
     b[0, :8], b[0, 8:16] = a[0, 8:16].copy(), a[0, :8].copy()   # swap two words
     ha, hb = api.frame_hash_host(a), api.frame_hash_host(b)
     assert ha[0] != hb[0] and ha[1] == hb[1]
+
+
+def test_header_is_c99_and_example_links(tmp_path, lib):
+    """include/mjpeg423_b200.h must be plain C (the reference is C99): the sample caller compiles with gcc -std=c99
+    -pedantic-errors and links against the shared library (no GPU needed to link)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = tmp_path / "decode_file"
+    pkg = os.path.join(ROOT, "mjpeg423-video-decoder-software_b200")
+    cmd = ["gcc", "-std=c99", "-pedantic-errors", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "decode_file.c"), "-L", pkg, "-lmjpeg423_b200", f"-Wl,-rpath,{pkg}", "-o", str(exe)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 2 and "usage" in out.stderr
