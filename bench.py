@@ -135,6 +135,28 @@ def reduce_over_ranks(dist, maxima, sums, device):
     return [float(x) for x in t.tolist()], [float(x) for x in c.tolist()]
 
 
+def gather_frames(dist, mine, counts, frame_bytes: int, root: int = 0):
+    """SURVEY.md 8e, the OPTIONAL single contiguous output: every rank's slice (`mine`: a flat uint8 tensor of
+    counts[rank] * frame_bytes) is sent to `root`, which receives them into ONE buffer in frame order -- grouped
+    point-to-point transfers (ncclSend / ncclRecv over NVLink with the nccl backend; the slices differ in length, so it
+    is not an all-gather).  Returns the contiguous tensor on root, None elsewhere."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if rank != root:
+        reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, root)])
+        for r in reqs:
+            r.wait()
+        return None
+    full = torch.empty(int(sum(counts)) * frame_bytes, dtype=torch.uint8, device=mine.device)
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64) * frame_bytes
+    ops = [dist.P2POp(dist.irecv, full[int(offs[r]):int(offs[r + 1])], r) for r in range(world) if r != root and counts[r]]
+    full[int(offs[root]):int(offs[root + 1])].copy_(mine)
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    return full
+
+
 def make_stream(wl: str, frames: int, nthreads: int):
     from mjpeg423_b200 import synth
     W, H, _, uniq, amp, quant, _ = WORKLOADS[wl]
@@ -333,6 +355,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-seconds of work for the cpu_baseline sample")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", action="store_true",
+                    help="multi-GPU: also gather every rank's frames into one contiguous buffer on rank 0 over NCCL (timed separately)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -378,7 +402,12 @@ def main():
     if q is not None:
         dec.set_quant(q, q)
     info = dec.upload(mpg)
-    d_out = dec.device_alloc(my_frames * frame_bytes)
+    out_t = None
+    if args.gather and world > 1:
+        out_t = torch.empty(my_frames * frame_bytes, dtype=torch.uint8, device="cuda")   # NCCL needs a torch tensor
+        d_out = out_t.data_ptr()
+    else:
+        d_out = dec.device_alloc(my_frames * frame_bytes)
 
     def barrier():
         if world > 1:
@@ -446,6 +475,42 @@ def main():
     if not args.no_verify:
         tail = pin_out.array[-frame_bytes:].reshape(1, H, W, 4)
         assert api.frame_hash_host(tail)[0] == want[e2e_frames - 1], "end-to-end output differs from the oracle"
+
+    # ---- optional: one contiguous output on rank 0 (NCCL point-to-point over NVLink), timed on its own --------------------
+    gather = None
+    if out_t is not None:
+        cnt_t = torch.zeros(world, dtype=torch.int64, device="cuda")
+        cnt_t[rank] = my_frames
+        dist.all_reduce(cnt_t)
+        counts = [int(x) for x in cnt_t.tolist()]
+        if sum(counts) * frame_bytes > 100e9:
+            raise SystemExit("--gather: the contiguous output would not fit one GPU; use the 1080p-8192 workload")
+        full = gather_frames(dist, out_t, counts, frame_bytes)        # warm-up (allocates, connects)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            full = gather_frames(dist, out_t, counts, frame_bytes)
+        g1.record()
+        barrier()
+        g_ms = torch.tensor([g0.elapsed_time(g1) / 3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            ok = None
+            if not args.no_verify:
+                lo0 = 0
+                ok = True
+                for r, c in enumerate(counts):        # every rank decoded frames [0, c) of its own copy of the clip cycle
+                    got_r = dec.hash_frames(full.data_ptr() + lo0 * frame_bytes, frame_bytes, c)
+                    ok = ok and bool(np.array_equal(got_r, want_u[np.arange(c) % uniq]))
+                    lo0 += c
+                if not ok:
+                    raise SystemExit("gathered output differs from the oracle")
+            moved = (sum(counts) - counts[0]) * frame_bytes
+            gather = {"ms": float(g_ms.item()), "bytes": int(moved), "GBs": moved / float(g_ms.item()) / 1e6,
+                      "how": "grouped ncclSend/ncclRecv (torch.distributed.batch_isend_irecv) into one buffer on rank 0",
+                      "verified": ok}
+        del full
 
     # ---- reduce over ranks ----------------------------------------------------------------------------------------
     (ev_ms_max, wall_ms_max, e2e_s_max), (total_frames, total_launches, total_e2e_frames) = reduce_over_ranks(
@@ -524,10 +589,13 @@ def main():
             "segments": {"per_step": ps["segments"], "chain_fixups": ps["fixups"]},
             "cpu_baseline": cpu_baseline,
         }
+        if gather is not None:
+            line["gather"] = gather
         print(json.dumps(line), flush=True)
     pin_in.free()
     pin_out.free()
-    dec.device_free(d_out)
+    if out_t is None:
+        dec.device_free(d_out)
     dec.close()
     if world > 1:
         dist.barrier()

@@ -30,6 +30,11 @@ mine = oracle.port().decode_mpg(mpg, lo, hi - lo)                 # this rank's 
 h = torch.zeros(total, dtype=torch.int64)
 h[lo:hi] = torch.from_numpy(api.frame_hash_host(mine).view(np.int64))
 dist.all_reduce(h)                                                # verification only: ranges are disjoint
+# the optional single contiguous output (bench.py --gather): uneven slices, point-to-point into rank 0's buffer
+fb = mine[0].nbytes
+full = bench.gather_frames(dist, torch.from_numpy(np.ascontiguousarray(mine).reshape(-1)), [bench.shard_range(total, r, world)[1] - bench.shard_range(total, r, world)[0] for r in range(world)], fb)
+if rank == 0:
+    assert np.array_equal(full.numpy().reshape(total, 48, 64, 4), oracle.port().decode_mpg(mpg)), "gathered output differs"
 (tmax,), (frames, launches) = bench.reduce_over_ranks(dist, [10.0 * (rank + 1)], [hi - lo, 4 * (hi - lo)], "cpu")
 if rank == 0:
     full = api.frame_hash_host(oracle.port().decode_mpg(mpg)).view(np.int64)
