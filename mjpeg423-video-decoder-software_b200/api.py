@@ -339,9 +339,11 @@ class Decoder:
 
     # -- encoder: frames -> .mpg, the loop of LIB/encoder/mjpeg423_encoder.c:97-225 ----------
     def encode_frames(self, frames, max_I_interval: int = 1, fix_tail: bool = False, d_frames: int = 0,
-                      shape: tuple | None = None) -> np.ndarray:
+                      shape: tuple | None = None, out=None) -> np.ndarray:
         """frames: (n, H, W, 4) uint8 BGRA on the host -- or d_frames = device pointer with shape = (n, H, W).
-        Returns the .mpg bytes (byte-identical to the reference encoder up to its last 512 bytes)."""
+        `out`: optional PinnedBuffer / uint8 array that receives the file (pinned memory gives full PCIe speed; it must
+        hold the result, mjpeg423_b200_encode_bound() is always enough).  Returns the .mpg bytes (byte-identical to
+        the reference encoder up to its last 512 bytes)."""
         if d_frames:
             n, H, W = shape
             src, on_dev = d_frames, 1
@@ -349,8 +351,10 @@ class Decoder:
             fr = np.ascontiguousarray(frames, dtype=np.uint8)
             n, H, W, _ = fr.shape
             src, on_dev = fr.ctypes.data, 0
-        cap = self.lib.mjpeg423_b200_encode_bound(n, W, H)
-        out = np.empty(cap, dtype=np.uint8)
+        if out is None:
+            out = np.empty(self.lib.mjpeg423_b200_encode_bound(n, W, H), dtype=np.uint8)
+        elif isinstance(out, PinnedBuffer):
+            out = out.array
         ln = C.c_size_t(0)
         rc = self.lib.mjpeg423_b200_encode_frames(self.h, src, on_dev, n, W, H, max_I_interval, 1 if fix_tail else 0,
                                                   out.ctypes.data, out.size, C.byref(ln))

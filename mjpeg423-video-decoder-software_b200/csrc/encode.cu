@@ -8,17 +8,18 @@
 //                    8x8 forward LL&M DCT (LIB/encoder/fdct.c:17-161, rows then columns, int16 stores) ->
 //                    quantise (LIB/encoder/quantize.c:16: round(x / q), half away from zero) to ABSOLUTE
 //                    levels.  8 lanes per block position: lane = pixel row, then = coefficient column.
-//   k_enc_size       one warp per block: code length in bits of the block as I-frame block (DC differential
+//   k_enc_size       one THREAD per block: code length in bits of the block as I-frame block (DC differential
 //                    against the previous block of the plane, quantize.c:18-25) and as P-frame block (every
-//                    level differential against the previous frame, :33-42).
+//                    level differential against the previous frame, :33-42): 64-bit occupancy mask in zig-zag
+//                    order + sum of VLI sizes, the ZRLs from the gaps between set bits.
 //   k_enc_scan       exclusive scan of the block lengths of every (frame, plane, variant): bit offset of every
 //                    block inside its plane stream + the stream length.
 //   (host)           the I/P decision of mjpeg423_encoder.c:155-185 needs only the six stream lengths of
 //                    every frame: I when first frame, I not larger than P, or max_I_interval reached.
-//   k_enc_emit       one warp per block of the chosen variant: every lane forms the symbols of two zig-zag
-//                    positions (LIB/encoder/lossless_encode.c:30-138: 4-bit DC size / 4-bit run + 4-bit size,
-//                    JPEG VLI amplitude, ZRL = F0, END = 00 unless position 63 is coded), a warp scan places
-//                    them, and they are OR-ed into the zero-initialised output (MSB first).
+//   k_enc_emit       one thread per block of the chosen variant: walks the set bits of the mask and ORs the symbols
+//                    (LIB/encoder/lossless_encode.c:30-138: 4-bit DC size / 4-bit run + 4-bit size, JPEG VLI
+//                    amplitude, ZRL = F0, END = 00 unless position 63 is coded) into the zero-initialised output
+//                    (MSB first).
 // The quirk of output_rest() (lossless_encode.c:80-83: the last partial byte of every plane stream is written
 // as 0) is reproduced unless MJPEG423_ENC_FIX_TAIL is set.
 #include <algorithm>
@@ -138,85 +139,74 @@ __device__ __forceinline__ void vli(int x, uint32_t& size, uint32_t& amp) {
     size = min(32u - (uint32_t)__clz(a), 11u);
     amp = (uint32_t)(x > 0 ? x : x - 1) & ((1u << size) - 1u);
 }
-struct BlockSyms {
-    uint32_t len[2];       // code length of the symbols at zig-zag positions lane, lane + 32 (0: nothing coded there)
-    uint64_t bits[2];      // the code, right-aligned (up to 3 ZRLs + run/size + amplitude = 43 bits)
-    uint32_t end_bits;     // 8 when the block closes with END (warp-uniform)
-};
-// v0 / v1: the values to code at zig-zag positions lane / lane + 32 (position 0 = the DC symbol).
-__device__ __forceinline__ BlockSyms block_syms(int v0, int v1, uint32_t lane) {
-    BlockSyms s;
-    const uint32_t nz_lo = __ballot_sync(FULL_MASK, v0 != 0) | 1u;        // bit 0: the DC symbol anchors the first run
-    const uint32_t nz_hi = __ballot_sync(FULL_MASK, v1 != 0);
-    const uint64_t m = ((uint64_t)nz_hi << 32) | nz_lo;
-    s.end_bits = (nz_hi >> 31) ? 0u : 8u;                                 // lossless_encode.c:43,54
+// Inverse zig-zag: natural index -> zig-zag position (the unrolled loops below call it with constants, so it folds).
+__host__ __device__ constexpr int inv_zigzag(int n) {
+    constexpr uint8_t inv[64] = {0, 1, 5, 6, 14, 15, 27, 28, 2, 4, 7, 13, 16, 26, 29, 42, 3, 8, 12, 17, 25, 30, 41, 43, 9, 11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+    return inv[n];
+}
+
+// Occupancy of one block: `mask` bit k = the value coded at zig-zag position k (1..63) is non-zero (bit 0 is always set:
+// the DC symbol anchors the first run), `sizes` = sum of the VLI sizes of those values, `dc` = the value of the DC symbol.
+struct BlockOcc { uint64_t mask; uint32_t sizes; int dc; };
+// variant 0 = I frame (levels as they are, DC differential against the previous block), 1 = P frame (every level
+// differential against the previous frame, int16 wrap like the reference's DCTELEM stores).
+template <int VARIANT>
+__device__ __forceinline__ BlockOcc block_occ(const int16_t* __restrict__ cur, const int16_t* __restrict__ prev, bool first_block) {
+    uint32_t lo = 1u, hi = 0u, sizes = 0;
+    int dc = 0;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int v = h ? v1 : v0;
-        const uint32_t k = lane + 32u * h;
-        uint32_t size, amp;
-        vli(v, size, amp);
-        if (k == 0) {                                                     // output_DC :86-96
-            s.len[h] = 4u + size;
-            s.bits[h] = ((uint64_t)size << size) | amp;
-        } else if (v != 0) {                                              // output_ZRL / output_AC :98-112
-            const uint64_t below = m & ((1ull << k) - 1ull);
-            const uint32_t run = k - (63u - (uint32_t)__clzll((long long)below)) - 1u;
-            const uint32_t nzrl = run >> 4;
-            const uint64_t zrl = nzrl == 0 ? 0ull : nzrl == 1 ? 0xF0ull : nzrl == 2 ? 0xF0F0ull : 0xF0F0F0ull;
-            s.len[h] = 8u * nzrl + 8u + size;
-            s.bits[h] = (zrl << (8u + size)) | ((uint64_t)(((run & 15u) << 4) | size) << size) | amp;
-        } else {
-            s.len[h] = 0;
-            s.bits[h] = 0;
+    for (int r = 0; r < 8; r++) {
+        const uint4 c = __ldg(reinterpret_cast<const uint4*>(cur) + r);
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (VARIANT == 1) q = __ldg(reinterpret_cast<const uint4*>(prev) + r);
+        const uint32_t cw[4] = {c.x, c.y, c.z, c.w}, qw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int v = (k & 1) ? hi16(cw[k >> 1]) : lo16(cw[k >> 1]);
+            if (VARIANT == 1) v = (int)(int16_t)(v - ((k & 1) ? hi16(qw[k >> 1]) : lo16(qw[k >> 1])));       // quantize.c:38-39
+            const int n = r * 8 + k;
+            if (n == 0) {
+                if (VARIANT == 0 && !first_block) v = (int)(int16_t)(v - (int)cur[-64]);                     // quantize.c:22-24
+                dc = v;
+            } else {
+                const int zp = inv_zigzag(n);
+                const uint32_t bit = v != 0 ? 1u : 0u;
+                if (zp < 32) lo |= bit << zp; else hi |= bit << (zp - 32);
+                sizes += min(32u - (uint32_t)__clz((uint32_t)abs(v)), 11u);
+            }
         }
     }
-    return s;
+    return BlockOcc{((uint64_t)hi << 32) | lo, sizes, dc};
 }
-
-// Values to code for block b of plane p of frame f: variant 0 = I frame, 1 = P frame.
-__device__ __forceinline__ void block_values(const int16_t* __restrict__ levels, uint32_t nb, uint32_t f, uint32_t p,
-                                             uint32_t b, uint32_t lane, int variant, int& v0, int& v1) {
-    const int16_t* cur = levels + (((size_t)f * 3 + p) * nb + b) * 64;
-    const uint32_t n0 = c_enc_zigzag[lane], n1 = c_enc_zigzag[lane + 32];
-    int a0 = cur[n0], a1 = cur[n1];
-    if (variant == 0) {
-        if (lane == 0 && b != 0) a0 = (int)(int16_t)(a0 - cur[-64]);       // DC differential (quantize.c:22-24)
-    } else {
-        const int16_t* prev = cur - (size_t)3 * nb * 64;                   // same plane of the previous frame
-        a0 = (int)(int16_t)(a0 - prev[n0]);                                // quantize.c:38-39
-        a1 = (int)(int16_t)(a1 - prev[n1]);
+// Code length of the block: DC symbol + (8 + size) per coded AC + 8 per ZRL + END unless position 63 is coded.
+__device__ __forceinline__ uint32_t block_length(const BlockOcc& o) {
+    uint32_t bits = 4u + min(32u - (uint32_t)__clz((uint32_t)abs(o.dc)), 11u) + o.sizes;
+    uint64_t m = o.mask & ~1ull;
+    bits += 8u * (uint32_t)__popcll(m) + ((o.mask >> 63) ? 0u : 8u);                  // lossless_encode.c:43,54
+    int prev = 0;
+    while (m) {
+        const int k = __ffsll((long long)m) - 1;
+        bits += 8u * (uint32_t)((k - prev - 1) >> 4);                                  // output_ZRL per 16 zeros
+        prev = k;
+        m &= m - 1;
     }
-    v0 = a0; v1 = a1;
-}
-
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
-#pragma unroll
-    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
-    return v;
+    return bits;
 }
 
 // block_bits: [frame][variant][plane][block] u32.  `levels` points at the chunk's first frame; frame -1 (the
 // previous chunk's last frame) precedes it in memory.  first_has_prev = 0 when frame 0 is the very first frame.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_enc_size(const int16_t* __restrict__ levels, uint32_t* __restrict__ block_bits, uint32_t nb, uint32_t n_frames,
            int first_has_prev) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t w = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint64_t w = (uint64_t)blockIdx.x * 128 + threadIdx.x;
     const uint64_t total = (uint64_t)n_frames * 3 * nb;
     if (w >= total) return;
     const uint32_t f = (uint32_t)(w / ((uint64_t)3 * nb)), rem = (uint32_t)(w % ((uint64_t)3 * nb));
     const uint32_t p = rem / nb, b = rem % nb;
-    for (int variant = 0; variant < 2; variant++) {
-        uint32_t bits = 0;
-        if (variant == 0 || f != 0 || first_has_prev) {
-            int v0, v1;
-            block_values(levels, nb, f, p, b, lane, variant, v0, v1);
-            const BlockSyms s = block_syms(v0, v1, lane);
-            bits = warp_sum(s.len[0] + s.len[1]) + s.end_bits;
-        }
-        if (lane == 0) block_bits[(((size_t)f * 2 + variant) * 3 + p) * nb + b] = bits;
-    }
+    const int16_t* cur = levels + w * 64;                                  // [frame][plane][block][64]
+    const int16_t* prev = cur - (size_t)3 * nb * 64;                       // same plane of the previous frame
+    block_bits[(((size_t)f * 2 + 0) * 3 + p) * nb + b] = block_length(block_occ<0>(cur, prev, b == 0));
+    block_bits[(((size_t)f * 2 + 1) * 3 + p) * nb + b] = (f != 0 || first_has_prev) ? block_length(block_occ<1>(cur, prev, false)) : 0u;
 }
 
 // In-place exclusive scan of every (frame, variant, plane) row of block_bits; totals[row] = stream length in bits.
@@ -273,31 +263,46 @@ __device__ __forceinline__ void or_bits(uint32_t* __restrict__ words, uint64_t p
     if (w2) atomicOr(words + w + 2, __byte_perm(w2, 0, 0x0123));
 }
 
-__global__ void __launch_bounds__(256)
+// The value coded at zig-zag position k (>= 1) of the block: re-read from the levels (L1-resident: the thread has just
+// read the whole block).
+__device__ __forceinline__ int coded_value(const int16_t* __restrict__ cur, const int16_t* __restrict__ prev, int k, int variant) {
+    const int n = c_enc_zigzag[k];
+    const int v = cur[n];
+    return variant ? (int)(int16_t)(v - prev[n]) : v;
+}
+
+__global__ void __launch_bounds__(128)
 k_enc_emit(const int16_t* __restrict__ levels, const uint32_t* __restrict__ block_off, const EncFrame* __restrict__ table,
            uint32_t* __restrict__ out_words, uint32_t nb, uint32_t n_frames, int fix_tail) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t w = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint64_t w = (uint64_t)blockIdx.x * 128 + threadIdx.x;
     const uint64_t total = (uint64_t)n_frames * 3 * nb;
     if (w >= total) return;
     const uint32_t f = (uint32_t)(w / ((uint64_t)3 * nb)), rem = (uint32_t)(w % ((uint64_t)3 * nb));
     const uint32_t p = rem / nb, b = rem % nb;
     const EncFrame ef = table[f];
-    int v0, v1;
-    block_values(levels, nb, f, p, b, lane, (int)ef.variant, v0, v1);
-    const BlockSyms s = block_syms(v0, v1, lane);
-    // exclusive scans of the symbol lengths in zig-zag order: positions 0..31, then 32..63
-    uint32_t i0 = s.len[0], i1 = s.len[1];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t a0 = __shfl_up_sync(FULL_MASK, i0, d), a1 = __shfl_up_sync(FULL_MASK, i1, d);
-        if (lane >= (uint32_t)d) { i0 += a0; i1 += a1; }
-    }
-    const uint32_t tot_lo = __shfl_sync(FULL_MASK, i0, 31);
-    const uint64_t base = ef.bit_off[p] + block_off[(((size_t)f * 2 + ef.variant) * 3 + p) * nb + b];
+    const int16_t* cur = levels + w * 64;
+    const int16_t* prev = cur - (size_t)3 * nb * 64;
+    const int variant = (int)ef.variant;
+    const BlockOcc o = variant ? block_occ<1>(cur, prev, false) : block_occ<0>(cur, prev, b == 0);
+    uint64_t pos = ef.bit_off[p] + block_off[(((size_t)f * 2 + ef.variant) * 3 + p) * nb + b];
     const uint64_t limit = ef.bit_off[p] + (fix_tail ? (uint64_t)ef.bits[p] : (uint64_t)(ef.bits[p] & ~7u));
-    or_bits(out_words, base + (i0 - s.len[0]), s.len[0], s.bits[0], limit);
-    or_bits(out_words, base + tot_lo + (i1 - s.len[1]), s.len[1], s.bits[1], limit);
+    uint32_t size, amp;
+    vli(o.dc, size, amp);                                                          // output_DC :86-96
+    or_bits(out_words, pos, 4u + size, ((uint64_t)size << size) | amp, limit);
+    pos += 4u + size;
+    uint64_t m = o.mask & ~1ull;
+    int last = 0;
+    while (m) {                                                                    // output_ZRL / output_AC :98-112
+        const int k = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const uint32_t run = (uint32_t)(k - last - 1), nzrl = run >> 4;
+        last = k;
+        vli(coded_value(cur, prev, k, variant), size, amp);
+        const uint64_t zrl = nzrl == 0 ? 0ull : nzrl == 1 ? 0xF0ull : nzrl == 2 ? 0xF0F0ull : 0xF0F0F0ull;
+        const uint32_t len = 8u * nzrl + 8u + size;
+        or_bits(out_words, pos, len, (zrl << (8u + size)) | ((uint64_t)(((run & 15u) << 4) | size) << size) | amp, limit);
+        pos += len;
+    }
     // END is eight zero bits: the buffer is zero-initialised, nothing to write.
 }
 
@@ -315,7 +320,7 @@ cudaError_t launch_enc_size(const int16_t* d_levels, uint32_t* d_block_bits, uin
                             uint32_t n_frames, int first_has_prev, cudaStream_t s) {
     const uint64_t warps = (uint64_t)n_frames * 3 * nb;
     if (!warps) return cudaSuccess;
-    k_enc_size<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(d_levels, d_block_bits, nb, n_frames, first_has_prev);
+    k_enc_size<<<(unsigned)((warps + 127) / 128), 128, 0, s>>>(d_levels, d_block_bits, nb, n_frames, first_has_prev);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     k_enc_scan<<<n_frames * 6, 256, 0, s>>>(d_block_bits, d_totals, nb);
@@ -325,7 +330,7 @@ cudaError_t launch_enc_emit(const int16_t* d_levels, const uint32_t* d_block_off
                             uint32_t nb, uint32_t n_frames, int fix_tail, cudaStream_t s) {
     const uint64_t warps = (uint64_t)n_frames * 3 * nb;
     if (!warps) return cudaSuccess;
-    k_enc_emit<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(d_levels, d_block_off, (const EncFrame*)d_table,
+    k_enc_emit<<<(unsigned)((warps + 127) / 128), 128, 0, s>>>(d_levels, d_block_off, (const EncFrame*)d_table,
                                                             (uint32_t*)d_out, nb, n_frames, fix_tail);
     return cudaGetLastError();
 }
