@@ -217,19 +217,59 @@ k_decode_fused(const uint2* __restrict__ blk_info,
         preC[0] = npreC[0]; preC[1] = npreC[1];
         load_info(tile + tile_step, ninfo);
 
-        bool cb_flat = false;                                            // warp-uniform: every Cb block of the tile is DC-only
+        bool cb_flat = false;                                            // warp-uniform: every Cb block of the tile is DC-only;
+        uint32_t cb_s8 = 0;                                              // its sample then waits here, not in the stash
 #pragma unroll 1
         for (int p = 0; p < 3; p++) {
-            // ---- scatter this plane's blocks into the (zeroed) transposed coefficient slots -----------------
-#pragma unroll
-            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(my_coef + c * (FUSED_TPB * 16)) = make_uint4(0, 0, 0, 0);
             // (p is a loop variable: select the pre-fetched registers without dynamic indexing)
             const uint32_t pmeta = p == 0 ? meta[0] : p == 1 ? meta[1] : meta[2];
             const uint32_t x = p == 0 ? lx[0] : p == 1 ? lx[1] : lx[2];
             const uint32_t xe = p == 0 ? lxe[0] : p == 1 ? lxe[1] : lxe[2];
             const uint2* zq = s_zq + (p ? 64 : 0);
-            *reinterpret_cast<int16_t*>(my_coef) = (int16_t)((int)(int16_t)(pmeta & 0xFFFFu) * (int)(zq[0].x >> 16));  // lossless_decode.c:94-95
+            const int dc_coef = (int)(int16_t)((int)(int16_t)(pmeta & 0xFFFFu) * (int)(zq[0].x >> 16));   // lossless_decode.c:94-95
             if (p == 1) prefetch_lists();                                 // next tile's lists (its index arrived during plane 0)
+
+            // emit(r, w0, w1): Y and Cb rows go to the stash, a Cr row completes 8 pixels.
+            auto emit = [&](int r, uint32_t w0, uint32_t w1) {
+                if (p < 2) {
+                    s_stash[(p * 16 + 2 * r) * FUSED_TPB + t] = w0;
+                    s_stash[(p * 16 + 2 * r + 1) * FUSED_TPB + t] = w1;
+                } else if (live) {
+                    colour_row_store(s_stash[(2 * r) * FUSED_TPB + t], s_stash[(2 * r + 1) * FUSED_TPB + t],
+                                     s_stash[(16 + 2 * r) * FUSED_TPB + t], s_stash[(17 + 2 * r) * FUSED_TPB + t], w0, w1,
+                                     dst + (size_t)r * W * 4);
+                }
+            };
+            // A plane whose 32 blocks are all DC-only: both passes collapse to (4*dc + 16) >> 5 (see idct_block()).
+            auto dc_only_plane = [&]() {
+                const uint32_t s8 = clamp255(((dc_coef << 2) + 16) >> 5);
+                const uint32_t v = s8 * 0x01010101u;
+                if (p == 1) { cb_flat = true; cb_s8 = s8; return; }       // kept in a register until Cr is known
+                if (p == 2 && cb_flat) {
+                    // Flat Cb and Cr blocks: the chroma terms are per-block constants.
+                    if (live) {
+                        const FlatChroma fc(cb_s8, s8);
+#pragma unroll 2
+                        for (int r = 0; r < 8; r++)
+                            fc.row_store(s_stash[(2 * r) * FUSED_TPB + t], s_stash[(2 * r + 1) * FUSED_TPB + t],
+                                         dst + (size_t)r * W * 4);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int r = 0; r < 8; r++) emit(r, v, v);
+                }
+            };
+            if (!__any_sync(FULL_MASK, xe != x)) { dc_only_plane(); continue; }   // no AC entry in the whole tile: nothing to scatter
+            if (p == 2 && cb_flat) {                                      // Cr needs the IDCT after all: materialise the flat Cb rows
+                const uint32_t v = cb_s8 * 0x01010101u;
+#pragma unroll 1
+                for (int r = 0; r < 16; r++) s_stash[(16 + r) * FUSED_TPB + t] = v;
+                cb_flat = false;
+            }
+            // ---- scatter this plane's blocks into the (zeroed) transposed coefficient slots -----------------
+#pragma unroll
+            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(my_coef + c * (FUSED_TPB * 16)) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<int16_t*>(my_coef) = (int16_t)dc_coef;
             __syncwarp();
             // The WARP reads each run with coalesced loads, and whichever lane holds an entry dequantises it and
             // stores it into the slot of the lane that owns the block (entry bits 6..10, written by
@@ -274,39 +314,7 @@ k_decode_fused(const uint2* __restrict__ blk_info,
             const uint32_t m_all = warp_or(m_bits);                       // warp-uniform from here on
             const uint32_t acm = m_all >> 8, anym = m_all & 0xFFu;
 
-            // emit(r, w0, w1): Y and Cb rows go to the stash, a Cr row completes 8 pixels.
-            auto emit = [&](int r, uint32_t w0, uint32_t w1) {
-                if (p < 2) {
-                    s_stash[(p * 16 + 2 * r) * FUSED_TPB + t] = w0;
-                    s_stash[(p * 16 + 2 * r + 1) * FUSED_TPB + t] = w1;
-                } else if (live) {
-                    colour_row_store(s_stash[(2 * r) * FUSED_TPB + t], s_stash[(2 * r + 1) * FUSED_TPB + t],
-                                     s_stash[(16 + 2 * r) * FUSED_TPB + t], s_stash[(17 + 2 * r) * FUSED_TPB + t], w0, w1,
-                                     dst + (size_t)r * W * 4);
-                }
-            };
-
-            if (((anym & 0xFEu) | (acm & 1u)) == 0) {
-                // DC-only blocks in the whole warp: both passes collapse to (4*dc + 16) >> 5 (see idct_block()).
-                const int dcv = (int)*reinterpret_cast<const int16_t*>(my_coef);
-                const uint32_t s8 = clamp255(((dcv << 2) + 16) >> 5);
-                const uint32_t v = s8 * 0x01010101u;
-                if (p == 1) cb_flat = true;
-                if (p == 2 && cb_flat) {
-                    // Flat Cb and Cr blocks: the chroma terms are per-block constants.
-                    if (live) {
-                        const FlatChroma fc(s_stash[16 * FUSED_TPB + t] & 255u, s8);
-#pragma unroll 2
-                        for (int r = 0; r < 8; r++)
-                            fc.row_store(s_stash[(2 * r) * FUSED_TPB + t], s_stash[(2 * r + 1) * FUSED_TPB + t],
-                                         dst + (size_t)r * W * 4);
-                    }
-                } else {
-#pragma unroll 1
-                    for (int r = 0; r < 8; r++) emit(r, v, v);
-                }
-                continue;
-            }
+            if (((anym & 0xFEu) | (acm & 1u)) == 0) { dc_only_plane(); continue; }   // entries, but none outside the DC position
             // ---- pass 1: columns, two at a time (idct.c:41-109) --------------------------------------------------
             const bool high_half = (anym & 0xF0u) != 0;
             const int npair = high_half ? 4 : 2;
