@@ -273,22 +273,6 @@ __device__ __forceinline__ void idct_block(const uint4 (&rows)[8], uint32_t acma
 
 __device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_sync(0xFFFFFFFFu, v); }
 
-// YCbCr -> packed BGRA word: LIB/decoder/ycbcr_to_rgb.c:31-46.  NORMALIZE_RGB (:19): negative -> 0,
-// else >> 14 then cap at 255 == relu(min(t >> 14, 255)) (an arithmetic shift keeps the sign).
-// Word = B | G<<8 | R<<16 | A(0)<<24 (rgb_pixel_t, mjpeg423_types.h:56-61).
-// The "- 128" of Cb/Cr is folded into the constant term: (Y<<14) + k*(C-128) == Y*16384 + k*C - 128*k,
-// all exact in int32 (|value| < 2^24).
-__device__ __forceinline__ uint32_t ycc_to_bgra(uint32_t y, uint32_t cb, uint32_t cr) {
-    const int Y = (int)y, CB = (int)cb, CR = (int)cr;
-    const int r = Y * 16384 + 22970 * CR - 128 * 22970;
-    const int g = Y * 16384 - 5638 * CB - 11700 * CR + 128 * (5638 + 11700);
-    const int b = Y * 16384 + 29032 * CB - 128 * 29032;
-    const uint32_t R = (uint32_t)__vimin_s32_relu(r >> 14, 255);
-    const uint32_t G = (uint32_t)__vimin_s32_relu(g >> 14, 255);
-    const uint32_t B = (uint32_t)__vimin_s32_relu(b >> 14, 255);
-    return B | (G << 8) | (R << 16);
-}
-
 // 256-bit global store (sm_100+): one full 32-byte sector per lane.
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
@@ -296,7 +280,10 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
                  : "memory");
 }
 
-// ---- packed colour conversion -----------------------------------------------------------------------------
+// ---- packed colour conversion: LIB/decoder/ycbcr_to_rgb.c:26-49 ---------------------------------------------
+// R = (Y << 14) + 22970 (Cr - 128), G = (Y << 14) - 5638 (Cb - 128) - 11700 (Cr - 128), B = (Y << 14) + 29032 (Cb - 128)
+// (:33-37), each through NORMALIZE_RGB (:19): negative -> 0, else >> 14, capped at 255.  Pixel word = B | G << 8 |
+// R << 16 | A(0) << 24 (rgb_pixel_t, mjpeg423_types.h:56-61).
 // Because Y << 14 has no low bits, NORMALIZE_RGB((Y << 14) + k) == clamp(Y + (k >> 14), 0, 255) exactly
 // (arithmetic shift = floor; k = the chroma terms of ycbcr_to_rgb.c:33-37, |k >> 14| < 256).  Two pixels are
 // processed per register in signed 16-bit lanes: one VIADDMNMX.S16x2.RELU does the add and both clamps of a
