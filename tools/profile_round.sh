@@ -9,4 +9,4 @@ python bench.py --workload enc-1080p --impl reference --steps 2 > gpurun_out/ben
 # launch list of the bench command (times under ncu are cold-cache and serialised: only the SHARES are meaningful)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
-tools/ncu_gpu.sh $TAG 256 k_ 6 5
+tools/ncu_gpu.sh $TAG 1000 k_ 6 5
