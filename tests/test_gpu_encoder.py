@@ -110,3 +110,12 @@ def test_encode_from_device_frames(dec):
 def test_encode_errors(dec):
     with pytest.raises(RuntimeError):
         dec.encode_frames(np.zeros((1, 12, 16, 4), np.uint8))        # H not a multiple of 8
+
+
+def test_encode_matches_golden_reference_files(dec):
+    """The committed .mpg files written by the reference's real mjpeg423_encode() (tests/golden/golden_encoder.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_encoder.npz"))
+    for gop in (24, 1, 3):
+        got = dec.encode_frames(g["enc_frames"], gop)
+        assert np.array_equal(got[:-512], g[f"enc_mpg_gop{gop}"]), f"gop {gop}"
