@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """bench.py -- decoded frames/s of the MJPEG423 hot path on N B200s (one process per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 1080p|4k|480p|1080p-8192]
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 1080p|4k|4k-q1|480p|1080p-8192]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ... [--gather]
     python bench.py --impl reference ...      # the reference's own C functions on the host cores
+    python bench.py --workload enc-1080p      # the encoder (own metric: encoded frames/sec)
 
 One "step" = one pass of the hot path (entropy decode -> dequantise -> IDCT -> YCbCr->BGRA) over the
 rank's whole batch of frames.  `value` is timed with the compressed stream already resident in HBM
@@ -11,6 +12,11 @@ rank's whole batch of frames.  `value` is timed with the compressed stream alrea
 (mjpeg423_b200_decode_frames): pinned .mpg in, pinned BGRA frames out, H2D and D2H inside the timed
 region.  Frames are independent intra frames, so ranks shard by frame range with no collective
 ("weak": every rank decodes its own `frames` frames; the 1080p-8192 workload is the fixed-total variant).
+--gather additionally moves every rank's frames into ONE contiguous buffer on rank 0 (NCCL point-to-point over
+NVLink, SURVEY.md 8e "optional single contiguous output"), timed on its own and reported under "gather".
+The JSON line also carries "roofline" (dominant kernel: algorithmic bytes / its measured time vs the measured HBM
+peak), "stages" (every kernel the same way), "cpu_baseline" (N=1: the compiled reference on all host cores, bounded
+sample), "clocks" (nvidia-smi samples inside the timed region) and "gpu_launches".
 
 Prints ONE JSON line on rank 0.
 """
