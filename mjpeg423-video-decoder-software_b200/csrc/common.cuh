@@ -115,15 +115,18 @@ struct Parser {
         int e;             // WANT_E only: amplitude of the DC / coded AC coefficient (HUFF_EXTEND, :204); 0 for a
                            // size-0 DC symbol, unspecified for END / ZRL
     };
-    // Consume one symbol.  Returns true when it ended the block (the parser is then positioned on the
-    // next block's DC symbol).
+    // Consume one symbol -- and the END symbol (eight zero bits) when one follows it directly: END carries no
+    // information of its own, and folding it into the step of the symbol before it saves one of the ~4.7 steps of
+    // an average block for four more instructions per step.  (The block boundaries, i.e. the trajectory, are the
+    // same as with END as a step of its own.)  Returns true when the block ended (the parser is then positioned on
+    // the next block's DC symbol).
     template <bool WANT_E>
     __device__ __forceinline__ bool step(Sym& sym) {
         const uint32_t t = __funnelshift_l(w1, w0, fpos);               // next 32 stream bits
         const bool dc = nh == (uint32_t)-4;
         const uint32_t rs = __funnelshift_r(t, 0u, nh);                 // t >> (32 - header bits): the 4 / 8 header bits
         const uint32_t size = rs & 15u, run = rs >> 4;                  // run == 0 for a DC symbol (rs < 16)
-        const uint32_t fnew = fpos + size - nh;
+        const uint32_t len = size - nh;                                 // header + amplitude bits, <= 23
         if (WANT_E) {
             // amplitude: the `size` bits after the header, JPEG VLI sign extension (HUFF_EXTEND): a field whose
             // top bit is clear stands for field - 2^size + 1.  size 0 gives 0.
@@ -133,16 +136,19 @@ struct Parser {
         } else {
             sym.e = 0;
         }
+        const bool szd = size != 0u || dc;
+        const bool coded = size != 0u && !dc;                           // a non-zero AC coefficient
+        const uint32_t at = (idx + (szd ? run : 16u)) & 255u;           // DC: idx (1); ZRL: idx + 16; coefficient: its index
+        const bool end0 = (!szd && run != 15u) || (coded && at >= 63u); // END / coefficient 63
+        const bool end_next = !end0 && ((t << len) >> 24) == 0u;        // ... or an END right behind this symbol
+        const uint32_t fnew = fpos + len + (end_next ? 8u : 0u);        // <= 31 bits: at most one word crossing
         if ((fpos ^ fnew) & rmask) {                                    // crossed into w1: fetch the word after w2
             w0 = w1;
             w1 = __byte_perm(w2, 0, 0x0123);
             w2 = __ldg(wp);
             wp++;
         }
-        const bool szd = size != 0u || dc;
-        const bool coded = size != 0u && !dc;                           // a non-zero AC coefficient
-        const uint32_t at = (idx + (szd ? run : 16u)) & 255u;           // DC: idx (1); ZRL: idx + 16; coefficient: its index
-        const bool end = (!szd && run != 15u) || (coded && at >= 63u) || fnew >= flim;   // END / coefficient 63 / guard
+        const bool end = end0 || end_next || fnew >= flim;              // ... or the guard
         idx = end ? 1u : at + (coded ? 1u : 0u);
         nh = end ? (uint32_t)-4 : (uint32_t)-8;
         fpos = fnew;
