@@ -77,6 +77,7 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     j.d_streams = d_sd;
     j.stream_lo = 0; j.n_streams = 1;
     j.seg_lo = 0; j.seg_hi = nseg_pad;
+    j.fold_end = (uint64_t)len * 8 < (uint64_t)num_blocks * 64;
     uint32_t* seg = s_seg.as<uint32_t>();
     CUX(cudaMemsetAsync(seg + 5 * (size_t)nseg_pad, 0, (size_t)nseg_pad * 4, s));   // every segment belongs to stream 0
     j.d_seg_stream = seg + 5 * (size_t)nseg_pad;

@@ -118,9 +118,10 @@ struct Parser {
     // Consume one symbol -- and the END symbol (eight zero bits) when one follows it directly: END carries no
     // information of its own, and folding it into the step of the symbol before it saves one of the ~4.7 steps of
     // an average block for four more instructions per step.  (The block boundaries, i.e. the trajectory, are the
-    // same as with END as a step of its own.)  Returns true when the block ended (the parser is then positioned on
-    // the next block's DC symbol).
-    template <bool WANT_E>
+    // same as with END as a step of its own, so passes with and without FOLD_END agree: the launchers turn it off
+    // for dense streams, where a block has tens of symbols and the look-ahead costs more than the saved step.)
+    // Returns true when the block ended (the parser is then positioned on the next block's DC symbol).
+    template <bool WANT_E, bool FOLD_END = true>
     __device__ __forceinline__ bool step(Sym& sym) {
         const uint32_t t = __funnelshift_l(w1, w0, fpos);               // next 32 stream bits
         const bool dc = nh == (uint32_t)-4;
@@ -140,7 +141,7 @@ struct Parser {
         const bool coded = size != 0u && !dc;                           // a non-zero AC coefficient
         const uint32_t at = (idx + (szd ? run : 16u)) & 255u;           // DC: idx (1); ZRL: idx + 16; coefficient: its index
         const bool end0 = (!szd && run != 15u) || (coded && at >= 63u); // END / coefficient 63
-        const bool end_next = !end0 && ((t << len) >> 24) == 0u;        // ... or an END right behind this symbol
+        const bool end_next = FOLD_END && !end0 && ((t << len) >> 24) == 0u;   // ... or an END right behind this symbol
         const uint32_t fnew = fpos + len + (end_next ? 8u : 0u);        // <= 31 bits: at most one word crossing
         if ((fpos ^ fnew) & rmask) {                                    // crossed into w1: fetch the word after w2
             w0 = w1;

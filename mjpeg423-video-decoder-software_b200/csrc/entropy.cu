@@ -130,6 +130,7 @@ __device__ __forceinline__ SegCtx seg_ctx(const uint8_t* __restrict__ payload, c
 
 // Resolve slot t for entry E.  WARP-COLLECTIVE (lanes with nothing to resolve pass need = false): the
 // symbol loop is uniform, lanes without a merge to do are parked.  s0 = f position of the super's first bit.
+template <bool FOLD>
 __device__ __forceinline__ void resolve_super(SyncShared& sh, const uint8_t* base, uint32_t E, uint32_t s0, uint32_t ftotal,
                                               int t, bool need) {
     const uint32_t fstop_eos = eos_stop(ftotal);
@@ -175,7 +176,7 @@ __device__ __forceinline__ void resolve_super(SyncShared& sh, const uint8_t* bas
     }
     while (__any_sync(FULL_MASK, next_stop != NO_WORK)) {
         Parser::Sym y;
-        const bool end = ps.step<false>(y);
+        const bool end = ps.step<false, FOLD>(y);
         cnt += end ? 1u : 0u;
         if (end && ps.fpos >= next_stop) {               // rare: first block start past a boundary / end of stream
             const uint32_t pos = ps.fpos;
@@ -199,6 +200,7 @@ __device__ __forceinline__ void resolve_super(SyncShared& sh, const uint8_t* bas
 }
 
 // Supers [sup_lo, sup_hi) of the plan.
+template <bool FOLD>
 __global__ void __launch_bounds__(ENT_TPB)
 k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
                const uint32_t* __restrict__ seg_stream, uint32_t sup_lo, uint32_t sup_hi,
@@ -223,7 +225,7 @@ k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
         }
         while (__any_sync(FULL_MASK, next_stop != NO_WORK)) {
             Parser::Sym y;
-            const bool end = ps.step<false>(y);
+            const bool end = ps.step<false, FOLD>(y);
             cnt += end ? 1u : 0u;
             if (end && ps.fpos >= next_stop) {           // rare: a checkpoint boundary or the end of the stream passed
                 const uint32_t pos = ps.fpos;
@@ -245,7 +247,7 @@ k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
     const bool own = valid && t >= 1;
     const bool has_pred = own && c.seg != 0;             // same stream as slot t-1 (streams are SUPER-aligned)
     uint32_t E = has_pred ? s0 - SUPER_BITS + (sh.cp[NCK - 1][t - 1] >> 16) : c.bias;
-    resolve_super(sh, c.base, E, s0, ftotal, t, own);
+    resolve_super<FOLD>(sh, c.base, E, s0, ftotal, t, own);
     if (valid && t == 0) sh.tpos[SUPER][0] = s0 + (sh.cp[NCK - 1][0] >> 16);     // the halo keeps its speculative exit
     __syncthreads();
     // ---- round 2: re-merge where the predecessor's resolved exit differs from its speculative one ----------
@@ -254,7 +256,7 @@ k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
     const bool redo = own && E2 != E;
     if (__syncthreads_or(redo)) {
         if (redo) E = E2;
-        resolve_super(sh, c.base, E, s0, ftotal, t, redo);
+        resolve_super<FOLD>(sh, c.base, E, s0, ftotal, t, redo);
     }
     if (own) {
 #pragma unroll
@@ -360,6 +362,7 @@ k_entropy_chain(const uint8_t* __restrict__ payload, const StreamDesc* __restric
 constexpr int INDEX_TPB = 64;
 constexpr int INDEX_SLOTS = 64;      // segments per CTA
 
+template <bool FOLD>
 __global__ void __launch_bounds__(INDEX_TPB, 16)
 k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
                 const uint32_t* __restrict__ seg_stream, uint32_t seg_lo, uint32_t seg_hi,
@@ -408,7 +411,7 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
     grab((uint32_t)t);
     while (__any_sync(FULL_MASK, cnt != 0u)) {
         Parser::Sym y;
-        const bool end = ps.step<true>(y);
+        const bool end = ps.step<true, FOLD>(y);
         if (y.dc) { cur = pframe ? y.e : cur + y.e; o_blk = o; }
         if (y.coded && y.at < 64u) {                     // (a parked lane never sees a coded symbol)
 #pragma unroll
@@ -493,8 +496,13 @@ cudaError_t launch_entropy_sync(const EntropyJob& j, cudaStream_t s) {
     if (j.seg_hi <= j.seg_lo) return cudaSuccess;
     const uint32_t sup_lo = j.seg_lo / SUPER, sup_hi = j.seg_hi / SUPER;       // chunk ranges are SUPER-aligned (build_plan)
     const uint32_t n = sup_hi - sup_lo;
-    k_entropy_sync<<<(n + SYNC_OWN - 1) / SYNC_OWN, ENT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, sup_lo, sup_hi,
-                                                                    j.d_seg_entry, j.d_seg_exit, j.d_seg_cnt);
+    const unsigned grid = (n + SYNC_OWN - 1) / SYNC_OWN;
+    if (j.fold_end)
+        k_entropy_sync<true><<<grid, ENT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, sup_lo, sup_hi, j.d_seg_entry,
+                                                      j.d_seg_exit, j.d_seg_cnt);
+    else
+        k_entropy_sync<false><<<grid, ENT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, sup_lo, sup_hi, j.d_seg_entry,
+                                                       j.d_seg_exit, j.d_seg_cnt);
     return cudaGetLastError();
 }
 cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s) {
@@ -507,9 +515,15 @@ cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s) {
 cudaError_t launch_entropy_index(const EntropyJob& j, cudaStream_t s) {
     if (j.seg_hi <= j.seg_lo) return cudaSuccess;
     const uint32_t n = j.seg_hi - j.seg_lo;
-    k_entropy_index<<<(n + INDEX_SLOTS - 1) / INDEX_SLOTS, INDEX_TPB, 0, s>>>(
-        j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry, j.d_seg_cnt, j.d_seg_first, j.d_seg_dc,
-        j.d_blk_info, j.d_sym, j.sym_seg0, j.d_fixups + 1);
+    const unsigned grid = (n + INDEX_SLOTS - 1) / INDEX_SLOTS;
+    if (j.fold_end)
+        k_entropy_index<true><<<grid, INDEX_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry,
+                                                         j.d_seg_cnt, j.d_seg_first, j.d_seg_dc, j.d_blk_info, j.d_sym, j.sym_seg0,
+                                                         j.d_fixups + 1);
+    else
+        k_entropy_index<false><<<grid, INDEX_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry,
+                                                          j.d_seg_cnt, j.d_seg_first, j.d_seg_dc, j.d_blk_info, j.d_sym, j.sym_seg0,
+                                                          j.d_fixups + 1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     k_entropy_dcscan<<<(j.n_streams + 3) / 4, 128, 0, s>>>(j.d_streams + j.stream_lo, j.n_streams, j.d_seg_dc);

@@ -352,6 +352,11 @@ EntropyJob make_job(const Plan& plan, const Tables& t, const uint8_t* d_payload_
     j.d_streams = t.streams;
     j.d_seg_stream = t.seg_stream;
     j.seg_lo = plan.f_seg0[f0]; j.seg_hi = plan.f_seg0[f1];
+    {   // fold END symbols into the previous step unless the chunk is dense: break-even is ~7 symbols (~64 bits) per block
+        uint64_t bytes = 0;
+        for (uint32_t f = f0; f < f1; f++) bytes += plan.frames[f].ysize + plan.frames[f].cbsize + plan.frames[f].crsize;
+        j.fold_end = bytes * 8 < (uint64_t)(f1 - f0) * 3 * plan.nb * 64;
+    }
     j.stream_lo = f0 * 3; j.n_streams = (f1 - f0) * 3;
     j.d_seg_entry = t.seg_entry; j.d_seg_exit = t.seg_exit; j.d_seg_cnt = t.seg_cnt; j.d_seg_first = t.seg_first;
     j.d_seg_dc = t.seg_dc;

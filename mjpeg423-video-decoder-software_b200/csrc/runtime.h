@@ -20,6 +20,8 @@ struct EntropyJob {
     const StreamDesc* d_streams = nullptr;       // plan-wide table
     const uint32_t* d_seg_stream = nullptr;      // plan-wide: global segment -> stream
     uint32_t seg_lo = 0, seg_hi = 0;             // global segments of the chunk
+    bool fold_end = true;                        // Parser::step look-ahead for END symbols: pays for sparse streams (few
+                                                 // symbols per block), costs for dense ones; same trajectory either way
     uint32_t stream_lo = 0, n_streams = 0;       // streams of the chunk (chain kernel: one CTA each)
     uint32_t *d_seg_entry = nullptr, *d_seg_exit = nullptr, *d_seg_cnt = nullptr, *d_seg_first = nullptr; // plan-wide
     uint32_t* d_seg_dc = nullptr;                // plan-wide: DC total, then DC predictor, of every segment
