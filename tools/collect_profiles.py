@@ -20,7 +20,8 @@ if os.path.exists(rep):
     out = os.path.join(P, f"{tag}_ncu_full_pipeline_1080p_{FRAMES}f.csv")
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, out], check=True, stdout=subprocess.DEVNULL)
     rows = list(csv.reader(open(out)))
-    names = rows[0][2:]
+    import re
+    names = [re.sub(r"<.*", "", n.replace("void ", "")).strip() for n in rows[0][2:]]      # "void k_x<1>" -> "k_x"
     get = lambda m: [float(x.replace(",", "")) for x in next(r for r in rows if r[0] == m)[2:]]
     unit = lambda m: next(r for r in rows if r[0] == m)[1]
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
