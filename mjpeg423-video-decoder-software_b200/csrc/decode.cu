@@ -10,8 +10,9 @@
 //                   as it scatters zig-zag -> natural order (:122-126); the CTA then stores its 128
 //                   consecutive blocks as one contiguous, fully coalesced 16 KB run.
 //   k_decode_fused  the whole reference loop body, LIB/decoder/mjpeg423_decoder.c:110-124, for intra
-//                   frames: the thread scatters the Y, Cb and Cr block of one block position through the
-//                   same slot, runs the three IDCTs in registers (idct.c:22-181) and writes the 8x8
+//                   frames: a warp takes 32 block positions, reads the lists of their Y, Cb and Cr blocks with
+//                   coalesced loads and scatters them into the owners' shared-memory slots, every thread then runs
+//                   the three IDCTs of its position through shared memory (idct.c:22-181) and writes the 8x8
 //                   BGRA pixels (ycbcr_to_rgb.c:26-49).  Coefficients and samples never touch HBM:
 //                   the kernel reads the lists (4 bytes per coded coefficient + 8 per block) and writes
 //                   4 bytes per pixel.

@@ -5,13 +5,12 @@
 // stream, for many fixed-size bitstream segments in parallel.  The code has no markers or restart
 // intervals, so segment entry points are found by self-synchronisation:
 //
-//   k_entropy_sync   a CTA owns a run of consecutive segments (of any number of streams).  Phase A parses
-//                    every segment speculatively from its first bit as if a block started there, leaving
-//                    NCP checkpoints (first block start at or after every CP_BITS boundary, blocks so far).
-//                    Phase B takes the predecessor's speculative exit as the segment's entry and parses
-//                    only until it MERGES with the recorded trajectory (same bit position at a block
-//                    start => identical future); a second round re-merges the segments whose
-//                    predecessor's exit moved.
+//   k_entropy_sync   a lane parses a super-segment (SUPER consecutive segments of one stream) speculatively
+//                    from its first bit as if a block started there, leaving checkpoints (first block start
+//                    at or after every CP_BITS boundary of the first segment and every segment boundary,
+//                    blocks so far).  Then the predecessor's exit is taken as the lane's entry and parsed only
+//                    until it MERGES with the recorded trajectory (same bit position at a block start =>
+//                    identical future); a second round re-merges the lanes whose predecessor's exit moved.
 //   k_entropy_chain  one CTA per stream: re-parses the few segments whose entry still differs from the
 //                    predecessor's resolved exit until the chain entry[i] == exit[i-1] holds from
 //                    entry[0] = 0 (correctness never rests on self-synchronisation, only speed does),
@@ -23,11 +22,9 @@
 //   k_entropy_dcscan exclusive scan (mod 2^16) of the segments' DC totals: the DC
 //                    predictor entering every segment.
 //
-// Every pass advances with Parser::step() (common.cuh) in a UNIFORM loop: one symbol per iteration for
+// Every pass advances with Parser::step() (common.cuh) in a UNIFORM loop: one step per iteration for
 // every lane, DC/AC and block-end handling predicated, the rare events (checkpoint, end of a job) in a
-// short divergent branch.  Work is handed out per LANE: segments (and merge jobs) are pulled from a
-// CTA-wide counter, so a lane whose segment is done starts the next one instead of idling until the
-// slowest lane of its warp finishes (symbols per segment vary by 2x with the picture content).
+// short divergent branch; a lane without work is parked.  Load balance comes from many small CTAs.
 #include "common.cuh"
 #include "runtime.h"
 
@@ -39,7 +36,7 @@ namespace mj {
 // DC levels are NOT tracked by the synchronisation passes (their symbol loop skips amplitudes altogether):
 // the index pass records every block's DC level relative to its segment's first block plus the segment's
 // DC total, k_entropy_dcscan turns the totals into the predictor entering each segment, and the decode
-// kernels add it (decode.cu: dc_pred()).
+// kernels add it (decode.cu: absolute_dc() / the prefetched predictors of k_decode_fused).
 
 // fstop_eos: a block start at or after this f position cannot hold a block any more (fewer than
 // MIN_BLOCK_BITS left): the stream's trailing pad bits.
