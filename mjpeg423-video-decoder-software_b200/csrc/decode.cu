@@ -157,49 +157,74 @@ k_decode_fused(const uint2* __restrict__ blk_info,
     const uint32_t warps_per_cta = FUSED_TPB / 32;
 
     // Block index entries (blk_info is the chunk's table: plane p of frame f starts at (f * 3 + p) * nb) are
-    // fetched one tile AHEAD, so that a tile starts with its list addresses known and only one load latency
-    // (the lists) is exposed instead of two dependent ones.
+    // fetched TWO tiles ahead and the head of every plane's lists ONE tile ahead, both right behind the scatter
+    // of the luminance plane: the IDCT of that plane (the one phase every tile has) then covers their latency.
+    // (ptxas tracks all global loads of this kernel with one scoreboard, so a wait for any of them waits for all
+    // that are in flight: nothing may be issued shortly before a point that consumes an older load.)
     const uint32_t tile_step = gridDim.x * warps_per_cta;
     const uint32_t lane = (uint32_t)t & 31u;
     uint8_t* warp_coef = s_coef + ((uint32_t)t & ~31u) * 16u;            // slot of lane 0 of this warp
     auto load_info = [&](uint32_t tile_, uint2 (&inf)[3]) {
         const uint32_t f_ = tile_ / tiles_per_frame;
         const uint32_t b_ = (tile_ - f_ * tiles_per_frame) * 32u + lane;
+        const bool ok = tile_ < n_tiles && b_ < nb;
 #pragma unroll
-        for (int p = 0; p < 3; p++)
-            inf[p] = (tile_ < n_tiles && b_ < nb) ? __ldg(blk_info + (size_t)(f_ * 3u + p) * nb + b_) : make_uint2(BLK_NO_SEG, 0u);
+        for (int p = 0; p < 3; p++) {                                    // (volatile: keeps its place behind the rotation below)
+            uint32_t vx = BLK_NO_SEG, vy = 0u;
+            if (ok) asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "l"(blk_info + (size_t)(f_ * 3u + p) * nb + b_));
+            inf[p] = make_uint2(vx, vy);
+        }
     };
     // The lists of consecutive blocks of a segment are consecutive in memory, so the 32 lists of a tile form
-    // one contiguous run of entries (a new run starts where the tile crosses into the next bitstream segment).
-    // first_run(): entry range [r0, r1) of the run that starts at lane 0; `rest` = first lanes of the other runs.
-    auto first_run = [&](uint32_t x, uint32_t xe, uint32_t& r0, uint32_t& r1, uint32_t& rest) {
+    // one contiguous run of entries per bitstream segment the tile touches (at the usual rates one or two).
+    // runs(): entry range [r0, r0 + n1) of the run that starts at lane 0, [s0, s0 + n2) of the second run
+    // (n2 = 0 without one); `rest` = first lanes of the runs after these.
+    auto runs = [&](uint32_t x, uint32_t xe, uint32_t& r0, uint32_t& n1, uint32_t& s0, uint32_t& n2, uint32_t& rest) {
         const uint32_t prev_e = __shfl_up_sync(FULL_MASK, xe, 1);
         rest = __ballot_sync(FULL_MASK, lane != 0u && x != prev_e);
         r0 = __shfl_sync(FULL_MASK, x, 0);
-        r1 = __shfl_sync(FULL_MASK, xe, rest ? __ffs(rest) - 2 : 31);
+        n1 = __shfl_sync(FULL_MASK, xe, rest ? __ffs(rest) - 2 : 31) - r0;
+        s0 = 0u; n2 = 0u;
+        if (rest) {
+            const int l2 = __ffs(rest) - 1;
+            rest &= rest - 1u;
+            s0 = __shfl_sync(FULL_MASK, x, l2);
+            n2 = __shfl_sync(FULL_MASK, xe, rest ? __ffs(rest) - 2 : 31) - s0;
+        }
     };
-    // The head of every plane's first run (4 x 32 luminance entries, 32 of each chrominance plane: most of a
-    // tile at the usual rates) is fetched one tile ahead as well, behind the IDCTs of the current tile.
-    constexpr int PRE_Y = 8;
-    uint2 ninfo[3];
+    // Entries carry their owner (the lane whose block they belong to), so ANY lane may process any entry: the
+    // head of a tile's entries -- slot v = v-th entry of the first run, continued in the second run -- is
+    // fetched into registers one tile ahead (4 x 32 luminance slots, 32 of each chrominance plane: all of a
+    // quiet tile), the remainder is staged through shared memory when the plane is decoded.
+    constexpr int PRE_Y = 4;
+    uint2 infoA[3], infoB[3];                                            // index entries of the next tile / the one after
     uint32_t npreY[PRE_Y], npreC[2], npred[3];
     auto prefetch_lists = [&]() {
 #pragma unroll
         for (int p = 0; p < 3; p++) {
-            npred[p] = ninfo[p].x == BLK_NO_SEG ? 0u : __ldg(seg_dc + ninfo[p].x / SYM_STRIDE);   // DC predictor of the block's segment
-            uint32_t r0, r1, rest;
-            first_run(ninfo[p].x, ninfo[p].x + (ninfo[p].y >> 16), r0, r1, rest);
+            npred[p] = infoA[p].x == BLK_NO_SEG ? 0u : __ldg(seg_dc + infoA[p].x / SYM_STRIDE);   // DC predictor of the block's segment
+            uint32_t r0, n1, s0, n2, rest;
+            runs(infoA[p].x, infoA[p].x + (infoA[p].y >> 16), r0, n1, s0, n2, rest);
+            const uint32_t d2 = s0 - n1 - r0;                            // slot v of the second run is entry r0 + d2 + v
             if (p == 0) {
 #pragma unroll
-                for (int i = 0; i < PRE_Y; i++) npreY[i] = lane + 32u * i < r1 - r0 ? __ldg(sym + (r0 + lane + 32u * i)) : 0u;
+                for (int i = 0; i < PRE_Y; i++) {
+                    const uint32_t v = lane + 32u * i;
+                    npreY[i] = v < n1 + n2 ? __ldg(sym + (r0 + v + (v < n1 ? 0u : d2))) : 0u;
+                }
             } else {
-                npreC[p - 1] = lane < r1 - r0 ? __ldg(sym + (r0 + lane)) : 0u;
+                npreC[p - 1] = lane < n1 + n2 ? __ldg(sym + (r0 + lane + (lane < n1 ? 0u : d2))) : 0u;
             }
         }
     };
+    // Staging area of the warp for list remainders: the lower half of its workspace granules (dead while a plane
+    // is scattered: pass 1 writes it, pass 2 reads it), 8 pieces of 512 bytes = 1024 entries.  Entry k = lane + 32 j
+    // is copied (cp.async, no register, no scoreboard) and read back by the SAME lane.
+    const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(smem) + ((uint32_t)t & ~31u) * 16u + lane * 4u;
     uint32_t tile = blockIdx.x * warps_per_cta + (uint32_t)(t >> 5);
-    load_info(tile, ninfo);
+    load_info(tile, infoA);
     prefetch_lists();
+    load_info(tile + tile_step, infoB);
 
     for (; tile < n_tiles; tile += tile_step) {
         const uint32_t f = tile / tiles_per_frame;
@@ -210,13 +235,12 @@ k_decode_fused(const uint2* __restrict__ blk_info,
         uint32_t meta[3], lx[3], lxe[3], preY[PRE_Y], preC[2];
 #pragma unroll
         for (int p = 0; p < 3; p++) {
-            lx[p] = ninfo[p].x; lxe[p] = ninfo[p].x + (ninfo[p].y >> 16);
-            meta[p] = (ninfo[p].y & 0xFFFF0000u) | ((ninfo[p].y + npred[p]) & 0xFFFFu);          // absolute DC level
+            lx[p] = infoA[p].x; lxe[p] = infoA[p].x + (infoA[p].y >> 16);
+            meta[p] = (infoA[p].y & 0xFFFF0000u) | ((infoA[p].y + npred[p]) & 0xFFFFu);          // absolute DC level
         }
 #pragma unroll
         for (int i = 0; i < PRE_Y; i++) preY[i] = npreY[i];
         preC[0] = npreC[0]; preC[1] = npreC[1];
-        load_info(tile + tile_step, ninfo);
 
         bool cb_flat = false;                                            // warp-uniform: every Cb block of the tile is DC-only;
         uint32_t cb_s8 = 0;                                              // its sample then waits here, not in the stash
@@ -228,7 +252,6 @@ k_decode_fused(const uint2* __restrict__ blk_info,
             const uint32_t xe = p == 0 ? lxe[0] : p == 1 ? lxe[1] : lxe[2];
             const uint2* zq = s_zq + (p ? 64 : 0);
             const int dc_coef = (int)(int16_t)((int)(int16_t)(pmeta & 0xFFFFu) * (int)(zq[0].x >> 16));   // lossless_decode.c:94-95
-            if (p == 1) prefetch_lists();                                 // next tile's lists (its index arrived during plane 0)
 
             // emit(r, w0, w1): Y and Cb rows go to the stash, a Cr row completes 8 pixels.
             auto emit = [&](int r, uint32_t w0, uint32_t w1) {
@@ -260,62 +283,82 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                     for (int r = 0; r < 8; r++) emit(r, v, v);
                 }
             };
-            if (!__any_sync(FULL_MASK, xe != x)) { dc_only_plane(); continue; }   // no AC entry in the whole tile: nothing to scatter
+            uint32_t m_all = 1u;                                          // column 0 always holds the DC coefficient
+            if (__any_sync(FULL_MASK, xe != x)) {                         // (no AC entry in the whole tile: nothing to scatter)
+                // ---- scatter this plane's blocks into the (zeroed) transposed coefficient slots -------------
+#pragma unroll
+                for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(my_coef + c * (FUSED_TPB * 16)) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<int16_t*>(my_coef) = (int16_t)dc_coef;
+                __syncwarp();
+                // Whichever lane holds an entry dequantises it and stores it into the slot of the lane that owns
+                // the block (entry bits 6..10, written by k_entropy_index): no lane waits for the longest list of
+                // the tile, no load depends on another.
+                uint32_t m_bits = 1u;
+                auto put = [&](uint32_t ent) {                            // dequantise + scatter one entry (:125)
+                    const uint2 z = zq[ent & 63u];
+                    *reinterpret_cast<int16_t*>(warp_coef + ((ent >> 2) & 0x1F0u) + (z.x & 0xFFFFu)) =
+                        (int16_t)(((int)ent >> 16) * (int)(z.x >> 16));
+                    m_bits |= z.y;
+                };
+                uint32_t r0, n1, s0, n2, rest;
+                runs(x, xe, r0, n1, s0, n2, rest);
+                uint32_t pre;                                             // slots already in registers
+                if (p == 0) {
+#pragma unroll
+                    for (int i = 0; i < PRE_Y; i++) if (lane + 32u * i < n1 + n2) put(preY[i]);
+                    pre = 32u * PRE_Y;
+                } else {
+                    if (lane < n1 + n2) put(p == 1 ? preC[0] : preC[1]);
+                    pre = 32u;
+                }
+                // Remainders (warp-uniform): of the first run, of the second run, then whole further runs.
+                const uint32_t u1 = min(n1, pre), u2 = min(pre - u1, n2);
+                uint32_t a = r0 + u1, e = r0 + n1, a2 = s0 + u2, e2 = s0 + n2;
+                for (;;) {
+                    while (a < e) {                                       // stage up to 1024 entries, then scatter them
+                        const uint32_t n = min(e - a, 1024u);
+                        const uint32_t* src = sym + a + lane;
+                        for (uint32_t j = 0; lane + 32u * j < n; j++)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(stage0 + (j >> 2) * (FUSED_TPB * 16u) + (j & 3u) * 128u),
+                                         "l"(src + 32u * j) : "memory");
+                        asm volatile("cp.async.wait_all;" ::: "memory");
+                        for (uint32_t j = 0; lane + 32u * j < n; j++) {
+                            uint32_t ent;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ent) : "r"(stage0 + (j >> 2) * (FUSED_TPB * 16u) + (j & 3u) * 128u) : "memory");
+                            put(ent);
+                        }
+                        a += n;
+                    }
+                    if (a2 < e2) { a = a2; e = e2; a2 = e2; continue; }
+                    if (!rest) break;
+                    const int l0 = __ffs(rest) - 1;
+                    rest &= rest - 1u;
+                    a = __shfl_sync(FULL_MASK, x, l0);
+                    e = __shfl_sync(FULL_MASK, xe, rest ? __ffs(rest) - 2 : 31);
+                }
+                __syncwarp();
+                m_all = warp_or(m_bits);                                  // warp-uniform from here on
+            }
+            if (p == 0) {                                                 // behind the luminance scatter: the pipeline advances
+                // (The rotation is spelled as opaque moves in front of the loads: otherwise the loads land in temporaries
+                // that are copied into the loop-carried registers at once, i.e. waited for right here.)
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    asm volatile("mov.b32 %0, %1;" : "=r"(infoA[q].x) : "r"(infoB[q].x));
+                    asm volatile("mov.b32 %0, %1;" : "=r"(infoA[q].y) : "r"(infoB[q].y));
+                }
+                prefetch_lists();
+                load_info(tile + 2u * tile_step, infoB);
+            }
+            const uint32_t acm = m_all >> 8, anym = m_all & 0xFFu;
+
+            if (((anym & 0xFEu) | (acm & 1u)) == 0) { dc_only_plane(); continue; }   // nothing outside the DC position
             if (p == 2 && cb_flat) {                                      // Cr needs the IDCT after all: materialise the flat Cb rows
                 const uint32_t v = cb_s8 * 0x01010101u;
 #pragma unroll 1
                 for (int r = 0; r < 16; r++) s_stash[(16 + r) * FUSED_TPB + t] = v;
                 cb_flat = false;
             }
-            // ---- scatter this plane's blocks into the (zeroed) transposed coefficient slots -----------------
-#pragma unroll
-            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(my_coef + c * (FUSED_TPB * 16)) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<int16_t*>(my_coef) = (int16_t)dc_coef;
-            __syncwarp();
-            // The WARP reads each run with coalesced loads, and whichever lane holds an entry dequantises it and
-            // stores it into the slot of the lane that owns the block (entry bits 6..10, written by
-            // k_entropy_index): no lane waits for the longest list of the tile, no load depends on another.
-            uint32_t m_bits = 1u;                                         // column 0 always holds the DC coefficient
-            auto put = [&](uint32_t ent) {                                // dequantise + scatter one entry (:125)
-                const uint2 z = zq[ent & 63u];
-                *reinterpret_cast<int16_t*>(warp_coef + ((ent >> 2) & 0x1F0u) + (z.x & 0xFFFFu)) =
-                    (int16_t)(((int)ent >> 16) * (int)(z.x >> 16));
-                m_bits |= z.y;
-            };
-            uint32_t r0, r1, rest, a;
-            first_run(x, xe, r0, r1, rest);
-            if (p == 0) {                                                 // head of the first run: already in registers
-#pragma unroll
-                for (int i = 0; i < PRE_Y; i++) if (lane + 32u * i < r1 - r0) put(preY[i]);
-                a = min(r0 + 32u * PRE_Y, r1);
-            } else {
-                if (lane < r1 - r0) put(p == 1 ? preC[0] : preC[1]);
-                a = min(r0 + 32u, r1);
-            }
-            for (;;) {                                                    // warp-uniform: rest of the run, then the other runs
-                for (; a < r1; a += 128u) {                               // four coalesced loads in flight
-                    const uint32_t i0 = a + lane, i1 = i0 + 32u, i2 = i0 + 64u, i3 = i0 + 96u;
-                    const uint32_t e0 = i0 < r1 ? __ldg(sym + i0) : 0u;
-                    const uint32_t e1 = i1 < r1 ? __ldg(sym + i1) : 0u;
-                    const uint32_t e2 = i2 < r1 ? __ldg(sym + i2) : 0u;
-                    const uint32_t e3 = i3 < r1 ? __ldg(sym + i3) : 0u;
-                    if (i0 < r1) put(e0);
-                    if (i1 < r1) put(e1);
-                    if (i2 < r1) put(e2);
-                    if (i3 < r1) put(e3);
-                }
-                if (!rest) break;
-                const int s0 = __ffs(rest) - 1;
-                rest &= rest - 1u;
-                r0 = __shfl_sync(FULL_MASK, x, s0);
-                r1 = __shfl_sync(FULL_MASK, xe, rest ? __ffs(rest) - 2 : 31);
-                a = r0;
-            }
-            __syncwarp();
-            const uint32_t m_all = warp_or(m_bits);                       // warp-uniform from here on
-            const uint32_t acm = m_all >> 8, anym = m_all & 0xFFu;
-
-            if (((anym & 0xFEu) | (acm & 1u)) == 0) { dc_only_plane(); continue; }   // entries, but none outside the DC position
             // ---- pass 1: columns, two at a time (idct.c:41-109) --------------------------------------------------
             const bool high_half = (anym & 0xF0u) != 0;
             const int npair = high_half ? 4 : 2;
