@@ -318,14 +318,24 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                     while (a < e) {                                       // stage up to 1024 entries, then scatter them
                         const uint32_t n = min(e - a, 1024u);
                         const uint32_t* src = sym + a + lane;
-                        for (uint32_t j = 0; lane + 32u * j < n; j++)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(stage0 + (j >> 2) * (FUSED_TPB * 16u) + (j & 3u) * 128u),
-                                         "l"(src + 32u * j) : "memory");
+                        const uint32_t ng = (n + 127u) >> 7;              // pieces of 128 entries
+                        for (uint32_t g = 0; g < ng; g++) {
+                            const uint32_t sa = stage0 + g * (FUSED_TPB * 16u), k = g * 128u + lane;
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                if (k + 32u * i < n)
+                                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + 128u * i), "l"(src + g * 128u + 32u * i) : "memory");
+                        }
                         asm volatile("cp.async.wait_all;" ::: "memory");
-                        for (uint32_t j = 0; lane + 32u * j < n; j++) {
-                            uint32_t ent;
-                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ent) : "r"(stage0 + (j >> 2) * (FUSED_TPB * 16u) + (j & 3u) * 128u) : "memory");
-                            put(ent);
+                        for (uint32_t g = 0; g < ng; g++) {
+                            const uint32_t sa = stage0 + g * (FUSED_TPB * 16u), k = g * 128u + lane;
+                            uint32_t ent[4];
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                if (k + 32u * i < n) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ent[i]) : "r"(sa + 128u * i) : "memory");
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                if (k + 32u * i < n) put(ent[i]);
                         }
                         a += n;
                     }
