@@ -131,7 +131,7 @@ k_decode_coef(const StreamDesc* __restrict__ streams, const uint32_t* __restrict
 //                          pass 1 reads a column with one LDS.128.)
 //   stash words [32][T]    word p*16 + 2r + h = samples of plane p (Y, Cb), row r, half h
 constexpr int FUSED_TPB = 576;                                   // 18 warps x 384 B/thread = 216 KB of the SM's 227 KB
-constexpr int FUSED_SMEM = FUSED_TPB * (256 + 128) + 2 * 64 * 8;
+constexpr int FUSED_SMEM = FUSED_TPB * (256 + 128) + 2 * 64 * 8 + 16;     // + the CTA's tile counter
 
 __global__ void __launch_bounds__(FUSED_TPB, 1)
 k_decode_fused(const uint2* __restrict__ blk_info,
@@ -143,7 +143,9 @@ k_decode_fused(const uint2* __restrict__ blk_info,
     uint8_t* s_coef = smem + 8 * FUSED_TPB * 16;                                    // granules 8..15
     uint32_t* s_stash = reinterpret_cast<uint32_t*>(smem + FUSED_TPB * 256);
     uint2* s_zq = reinterpret_cast<uint2*>(smem + FUSED_TPB * 384);                 // 2 x 64 entries
+    uint32_t* s_next = reinterpret_cast<uint32_t*>(smem + FUSED_TPB * 384 + 1024);  // tiles handed out so far
     const int t = threadIdx.x;
+    if (t == 0) *s_next = 0u;
     if (t < 128) {     // zig-zag index -> .x = transposed slot offset | quant << 16, .y = column bit | (row >= 1) column bit << 8
         const int tab = t >> 6, k = t & 63;
         const uint32_t n = c_zigzag[k], col = n & 7u, row = n >> 3;
@@ -154,15 +156,22 @@ k_decode_fused(const uint2* __restrict__ blk_info,
     uint8_t* my_coef = s_coef + t * 16;
     const uint32_t tiles_per_frame = (nb + 31u) / 32u;
     const uint32_t n_tiles = tiles_per_frame * n_frames;
-    const uint32_t warps_per_cta = FUSED_TPB / 32;
 
     // Block index entries (blk_info is the chunk's table: plane p of frame f starts at (f * 3 + p) * nb) are
     // fetched TWO tiles ahead and the head of every plane's lists ONE tile ahead, both right behind the scatter
     // of the luminance plane: the IDCT of that plane (the one phase every tile has) then covers their latency.
     // (ptxas tracks all global loads of this kernel with one scoreboard, so a wait for any of them waits for all
     // that are in flight: nothing may be issued shortly before a point that consumes an older load.)
-    const uint32_t tile_step = gridDim.x * warps_per_cta;
     const uint32_t lane = (uint32_t)t & 31u;
+    // Tiles are handed out DYNAMICALLY inside a CTA: CTA c owns tiles c, c + grid, c + 2 grid, ... and its warps take
+    // the next one from a shared-memory counter.  (18 warps on 4 schedulers: with a fixed share per warp the two
+    // schedulers that hold 5 warps set the kernel's duration while the other two idle for the last 15 % of it.)
+    // The counter is read at the top of a tile for the tile after the next (index entries are fetched two tiles ahead).
+    auto take = [&]() { return lane == 0u ? atomicAdd(s_next, 1u) : 0u; };          // raw: valid in lane 0
+    auto tile_of = [&](uint32_t raw) {
+        const unsigned long long k = __shfl_sync(FULL_MASK, raw, 0);
+        return (uint32_t)min(k * gridDim.x + blockIdx.x, (unsigned long long)n_tiles);
+    };
     uint8_t* warp_coef = s_coef + ((uint32_t)t & ~31u) * 16u;            // slot of lane 0 of this warp
     auto load_info = [&](uint32_t tile_, uint2 (&inf)[3]) {
         const uint32_t f_ = tile_ / tiles_per_frame;
@@ -221,12 +230,13 @@ k_decode_fused(const uint2* __restrict__ blk_info,
     // is scattered: pass 1 writes it, pass 2 reads it), 8 pieces of 512 bytes = 1024 entries.  Entry k = lane + 32 j
     // is copied (cp.async, no register, no scoreboard) and read back by the SAME lane.
     const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(smem) + ((uint32_t)t & ~31u) * 16u + lane * 4u;
-    uint32_t tile = blockIdx.x * warps_per_cta + (uint32_t)(t >> 5);
+    uint32_t tile = tile_of(take()), tile1 = tile_of(take()), tile2 = 0;  // current tile, the next one, the one after it
     load_info(tile, infoA);
     prefetch_lists();
-    load_info(tile + tile_step, infoB);
+    load_info(tile1, infoB);
 
-    for (; tile < n_tiles; tile += tile_step) {
+    for (; tile < n_tiles; tile = tile1, tile1 = tile2) {
+        const uint32_t raw2 = take();                                     // the tile after the next
         const uint32_t f = tile / tiles_per_frame;
         const uint32_t b = (tile - f * tiles_per_frame) * 32u + lane;
         const bool live = b < nb;
@@ -358,7 +368,8 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                     asm volatile("mov.b32 %0, %1;" : "=r"(infoA[q].y) : "r"(infoB[q].y));
                 }
                 prefetch_lists();
-                load_info(tile + 2u * tile_step, infoB);
+                tile2 = tile_of(raw2);
+                load_info(tile2, infoB);
             }
             const uint32_t acm = m_all >> 8, anym = m_all & 0xFFu;
 
