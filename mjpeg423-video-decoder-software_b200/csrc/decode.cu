@@ -212,6 +212,13 @@ k_decode_fused(const uint2* __restrict__ blk_info,
 #pragma unroll
         for (int p = 0; p < 3; p++) {
             npred[p] = infoA[p].x == BLK_NO_SEG ? 0u : __ldg(seg_dc + infoA[p].x / SYM_STRIDE);   // DC predictor of the block's segment
+            if (p == 0) {
+#pragma unroll
+                for (int i = 0; i < PRE_Y; i++) npreY[i] = 0u;
+            } else {
+                npreC[p - 1] = 0u;
+            }
+            if (!__any_sync(FULL_MASK, (infoA[p].y >> 16) != 0u)) continue;   // a plane without any entry (flat chrominance)
             uint32_t r0, n1, s0, n2, rest;
             runs(infoA[p].x, infoA[p].x + (infoA[p].y >> 16), r0, n1, s0, n2, rest);
             const uint32_t d2 = s0 - n1 - r0;                            // slot v of the second run is entry r0 + d2 + v
@@ -219,10 +226,10 @@ k_decode_fused(const uint2* __restrict__ blk_info,
 #pragma unroll
                 for (int i = 0; i < PRE_Y; i++) {
                     const uint32_t v = lane + 32u * i;
-                    npreY[i] = v < n1 + n2 ? __ldg(sym + (r0 + v + (v < n1 ? 0u : d2))) : 0u;
+                    if (v < n1 + n2) npreY[i] = __ldg(sym + (r0 + v + (v < n1 ? 0u : d2)));
                 }
             } else {
-                npreC[p - 1] = lane < n1 + n2 ? __ldg(sym + (r0 + lane + (lane < n1 ? 0u : d2))) : 0u;
+                if (lane < n1 + n2) npreC[p - 1] = __ldg(sym + (r0 + lane + (lane < n1 ? 0u : d2)));
             }
         }
     };
