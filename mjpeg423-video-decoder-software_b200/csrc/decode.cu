@@ -133,11 +133,19 @@ k_decode_coef(const StreamDesc* __restrict__ streams, const uint32_t* __restrict
 constexpr int FUSED_TPB = 576;                                   // 18 warps x 384 B/thread = 216 KB of the SM's 227 KB
 constexpr int FUSED_SMEM = FUSED_TPB * (256 + 128) + 2 * 64 * 8 + 16;     // + the CTA's tile counter
 
+//
+// PF = true is the variant for ranges that hold P frames (LIB/decoder/lossless_decode.c:90-92,121-123: every decoded
+// value is ADDED to the previous frame's coefficient).  A work item is then (tile, GOP): the warp walks the GOP's frames
+// in order for one tile, so the inter-frame state never leaves the warp: the DC values and the accumulated column
+// masks stay in registers, and the coefficient slots of a plane that has held an AC coefficient since the I frame are
+// parked between frames in a per-warp scratch area (12 KB per warp: it stays in L2) and brought back with cp.async.
+// gop_first[g] .. gop_first[g + 1] are the (chunk-relative) frames of GOP g.
+template <bool PF>
 __global__ void __launch_bounds__(FUSED_TPB, 1)
 k_decode_fused(const uint2* __restrict__ blk_info,
                const uint32_t* __restrict__ sym, const uint32_t* __restrict__ seg_dc,
                const int16_t* __restrict__ quant, uint8_t* __restrict__ out, uint32_t nb, uint32_t wb, uint32_t W,
-               uint32_t n_frames) {
+               uint32_t n_frames, const uint32_t* __restrict__ gop_first, uint32_t n_gops, uint4* __restrict__ state) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint4* s_ws = reinterpret_cast<uint4*>(smem);                                   // granules 0..15
     uint8_t* s_coef = smem + 8 * FUSED_TPB * 16;                                    // granules 8..15
@@ -155,7 +163,7 @@ k_decode_fused(const uint2* __restrict__ blk_info,
     __syncthreads();
     uint8_t* my_coef = s_coef + t * 16;
     const uint32_t tiles_per_frame = (nb + 31u) / 32u;
-    const uint32_t n_tiles = tiles_per_frame * n_frames;
+    const uint32_t n_items = tiles_per_frame * (PF ? n_gops : n_frames);  // work items: (tile, frame) / (tile, GOP)
 
     // Block index entries (blk_info is the chunk's table: plane p of frame f starts at (f * 3 + p) * nb) are
     // fetched TWO tiles ahead and the head of every plane's lists ONE tile ahead, both right behind the scatter
@@ -168,15 +176,25 @@ k_decode_fused(const uint2* __restrict__ blk_info,
     // schedulers that hold 5 warps set the kernel's duration while the other two idle for the last 15 % of it.)
     // The counter is read at the top of a tile for the tile after the next (index entries are fetched two tiles ahead).
     auto take = [&]() { return lane == 0u ? atomicAdd(s_next, 1u) : 0u; };          // raw: valid in lane 0
-    auto tile_of = [&](uint32_t raw) {
+    struct Pos { uint32_t f, tb, fend; };         // frame (chunk-relative; n_frames = nothing left), tile of the frame, end of the item
+    auto item_pos = [&](uint32_t raw) {
         const unsigned long long k = __shfl_sync(FULL_MASK, raw, 0);
-        return (uint32_t)min(k * gridDim.x + blockIdx.x, (unsigned long long)n_tiles);
+        const uint32_t i = (uint32_t)min(k * gridDim.x + blockIdx.x, (unsigned long long)n_items);
+        Pos q;
+        q.f = q.fend = n_frames; q.tb = 0u;
+        if (i < n_items) {
+            const uint32_t g = i / tiles_per_frame;
+            q.tb = i - g * tiles_per_frame;
+            if (PF) { q.f = __ldg(gop_first + g); q.fend = __ldg(gop_first + g + 1); }
+            else { q.f = g; q.fend = g + 1u; }
+        }
+        return q;
     };
     uint8_t* warp_coef = s_coef + ((uint32_t)t & ~31u) * 16u;            // slot of lane 0 of this warp
-    auto load_info = [&](uint32_t tile_, uint2 (&inf)[3]) {
-        const uint32_t f_ = tile_ / tiles_per_frame;
-        const uint32_t b_ = (tile_ - f_ * tiles_per_frame) * 32u + lane;
-        const bool ok = tile_ < n_tiles && b_ < nb;
+    auto load_info = [&](const Pos& q, uint2 (&inf)[3]) {
+        const uint32_t f_ = q.f;
+        const uint32_t b_ = q.tb * 32u + lane;
+        const bool ok = f_ < n_frames && b_ < nb;
 #pragma unroll
         for (int p = 0; p < 3; p++) {                                    // (volatile: keeps its place behind the rotation below)
             uint32_t vx = BLK_NO_SEG, vy = 0u;
@@ -237,15 +255,27 @@ k_decode_fused(const uint2* __restrict__ blk_info,
     // is scattered: pass 1 writes it, pass 2 reads it), 8 pieces of 512 bytes = 1024 entries.  Entry k = lane + 32 j
     // is copied (cp.async, no register, no scoreboard) and read back by the SAME lane.
     const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(smem) + ((uint32_t)t & ~31u) * 16u + lane * 4u;
-    uint32_t tile = tile_of(take()), tile1 = tile_of(take()), tile2 = 0;  // current tile, the next one, the one after it
-    load_info(tile, infoA);
+    // Positions: `cur` is decoded, `nxt` follows it (its index entries are in flight), `nn` follows that.  Inside an
+    // item (PF) the successor is the next frame of the GOP, otherwise the first frame of a newly taken item.
+    Pos cur = item_pos(take()), nxt, nn;
+    bool cur_first = true, nxt_first, nn_first = true;    // first frame of its item (an I frame: no state before it)
+    nxt_first = !(PF && cur.f + 1u < cur.fend);
+    if (nxt_first) nxt = item_pos(take());
+    else { nxt.f = cur.f + 1u; nxt.tb = cur.tb; nxt.fend = cur.fend; }
+    nn = nxt;
+    load_info(cur, infoA);
     prefetch_lists();
-    load_info(tile1, infoB);
+    load_info(nxt, infoB);
+    // PF: inter-frame state of the item -- DC coefficients (per lane) and accumulated masks (warp-uniform) of the planes
+    int dcY = 0, dcB = 0, dcR = 0;
+    uint32_t mY = 1u, mB = 1u, mR = 1u;
+    uint4* my_state = PF ? state + ((size_t)(blockIdx.x * (FUSED_TPB / 32) + (t >> 5)) * 3u * 8u) * 32u + lane : nullptr;
 
-    for (; tile < n_tiles; tile = tile1, tile1 = tile2) {
-        const uint32_t raw2 = take();                                     // the tile after the next
-        const uint32_t f = tile / tiles_per_frame;
-        const uint32_t b = (tile - f * tiles_per_frame) * 32u + lane;
+    for (; cur.f < n_frames; cur = nxt, nxt = nn, cur_first = nxt_first, nxt_first = nn_first) {
+        nn_first = !(PF && nxt.f + 1u < nxt.fend);
+        const uint32_t raw2 = nn_first ? take() : 0u;                     // the item after the next position's
+        const uint32_t f = cur.f;
+        const uint32_t b = cur.tb * 32u + lane;
         const bool live = b < nb;
         uint8_t* dst = out + ((size_t)f * nb * 64 + ((size_t)(b / wb) * 8 * W + (size_t)(b % wb) * 8)) * 4;
 
@@ -268,7 +298,16 @@ k_decode_fused(const uint2* __restrict__ blk_info,
             const uint32_t x = p == 0 ? lx[0] : p == 1 ? lx[1] : lx[2];
             const uint32_t xe = p == 0 ? lxe[0] : p == 1 ? lxe[1] : lxe[2];
             const uint2* zq = s_zq + (p ? 64 : 0);
-            const int dc_coef = (int)(int16_t)((int)(int16_t)(pmeta & 0xFFFFu) * (int)(zq[0].x >> 16));   // lossless_decode.c:94-95
+            int dc_coef = (int)(int16_t)((int)(int16_t)(pmeta & 0xFFFFu) * (int)(zq[0].x >> 16));   // lossless_decode.c:94-95
+            uint32_t macc = 1u;                                           // PF: columns occupied since the item's I frame
+            if (PF) {
+                if (!cur_first) {                                         // P frame: the level is a delta against the previous frame (:91)
+                    dc_coef = (int)(int16_t)(dc_coef + (p == 0 ? dcY : p == 1 ? dcB : dcR));
+                    macc = p == 0 ? mY : p == 1 ? mB : mR;
+                }
+                if (p == 0) dcY = dc_coef; else if (p == 1) dcB = dc_coef; else dcR = dc_coef;
+            }
+            const bool has_state = PF && (macc & 0xFFFEu) != 0u;          // the plane's slots are parked in the scratch area
 
             // emit(r, w0, w1): Y and Cb rows go to the stash, a Cr row completes 8 pixels.
             auto emit = [&](int r, uint32_t w0, uint32_t w1) {
@@ -300,11 +339,22 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                     for (int r = 0; r < 8; r++) emit(r, v, v);
                 }
             };
-            uint32_t m_all = 1u;                                          // column 0 always holds the DC coefficient
-            if (__any_sync(FULL_MASK, xe != x)) {                         // (no AC entry in the whole tile: nothing to scatter)
-                // ---- scatter this plane's blocks into the (zeroed) transposed coefficient slots -------------
+            uint32_t m_all = macc;                                        // column 0 always holds the DC coefficient
+            const bool has_ac = __any_sync(FULL_MASK, xe != x);
+            if (has_ac || has_state) {                                    // (no AC entry in the whole tile: nothing to scatter)
+                // ---- scatter this plane's blocks into the transposed coefficient slots: zeroed (the memset of :77-78)
+                // or, for a P frame, holding the previous frame's coefficients --------------------------------------
+                if (has_state) {
+                    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(my_coef);
 #pragma unroll
-                for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(my_coef + c * (FUSED_TPB * 16)) = make_uint4(0, 0, 0, 0);
+                    for (int c = 0; c < 8; c++)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + c * (FUSED_TPB * 16)),
+                                     "l"(my_state + (p * 8 + c) * 32) : "memory");
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(my_coef + c * (FUSED_TPB * 16)) = make_uint4(0, 0, 0, 0);
+                }
                 *reinterpret_cast<int16_t*>(my_coef) = (int16_t)dc_coef;
                 __syncwarp();
                 // Whichever lane holds an entry dequantises it and stores it into the slot of the lane that owns
@@ -313,8 +363,10 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                 uint32_t m_bits = 1u;
                 auto put = [&](uint32_t ent) {                            // dequantise + scatter one entry (:125)
                     const uint2 z = zq[ent & 63u];
-                    *reinterpret_cast<int16_t*>(warp_coef + ((ent >> 2) & 0x1F0u) + (z.x & 0xFFFFu)) =
-                        (int16_t)(((int)ent >> 16) * (int)(z.x >> 16));
+                    int16_t* d = reinterpret_cast<int16_t*>(warp_coef + ((ent >> 2) & 0x1F0u) + (z.x & 0xFFFFu));
+                    const int v = ((int)ent >> 16) * (int)(z.x >> 16);
+                    if (PF) *d = (int16_t)(v + (cur_first ? 0 : (int)*d));   // :122 (P frame: added) / :125 (I frame: stored)
+                    else *d = (int16_t)v;
                     m_bits |= z.y;
                 };
                 uint32_t r0, n1, s0, n2, rest;
@@ -365,7 +417,16 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                 }
                 __syncwarp();
                 m_all = warp_or(m_bits);                                  // warp-uniform from here on
+                if (PF) {
+                    m_all |= macc;
+                    if (has_ac && cur.f + 1u < cur.fend && (m_all & 0xFFFEu)) {   // park the slots for the item's next frame
+#pragma unroll
+                        for (int c = 0; c < 8; c++)
+                            my_state[(p * 8 + c) * 32] = *reinterpret_cast<const uint4*>(my_coef + c * (FUSED_TPB * 16));
+                    }
+                }
             }
+            if (PF) { if (p == 0) mY = m_all; else if (p == 1) mB = m_all; else mR = m_all; }
             if (p == 0) {                                                 // behind the luminance scatter: the pipeline advances
                 // (The rotation is spelled as opaque moves in front of the loads: otherwise the loads land in temporaries
                 // that are copied into the loop-carried registers at once, i.e. waited for right here.)
@@ -375,8 +436,9 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                     asm volatile("mov.b32 %0, %1;" : "=r"(infoA[q].y) : "r"(infoB[q].y));
                 }
                 prefetch_lists();
-                tile2 = tile_of(raw2);
-                load_info(tile2, infoB);
+                if (nn_first) nn = item_pos(raw2);
+                else { nn.f = nxt.f + 1u; nn.tb = nxt.tb; nn.fend = nxt.fend; }
+                load_info(nn, infoB);
             }
             const uint32_t acm = m_all >> 8, anym = m_all & 0xFFu;
 
@@ -437,23 +499,35 @@ cudaError_t launch_decode_coef(const EntropyJob& j, const uint32_t* d_stream_ids
                                            d_quant, d_coef);
     return cudaGetLastError();
 }
+// gop_first == nullptr: an intra-only range (one work item per tile and frame).  Otherwise the range holds P frames:
+// d_gop_first[0 .. n_gops] are the chunk-relative first frames of its GOPs (+ the end), d_state the per-warp scratch of
+// FUSED_STATE_BYTES (see k_decode_fused<true>).
 cudaError_t launch_decode_fused(const EntropyJob& j, const int16_t* d_quant, void* d_out, uint32_t n_frames,
-                                uint32_t W, uint32_t H, cudaStream_t s) {
+                                uint32_t W, uint32_t H, const uint32_t* d_gop_first, uint32_t n_gops, void* d_state,
+                                cudaStream_t s) {
     if (n_frames == 0) return cudaSuccess;
-    static int n_sm = 0;
-    if (!n_sm) {
-        cudaError_t e = cudaFuncSetAttribute(k_decode_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
-        if (e != cudaSuccess) return e;
-        int dev = 0;
-        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-        if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    static int n_sm[64] = {0};                                             // per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!n_sm[dev]) {
+        if ((e = cudaFuncSetAttribute(k_decode_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_decode_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        if (n_sm[dev] > FUSED_MAX_CTAS) n_sm[dev] = FUSED_MAX_CTAS;        // the scratch area is sized for this many
     }
     const uint32_t wb = W / 8, nb = wb * (H / 8);
-    const uint64_t n_tiles = (uint64_t)((nb + 31) / 32) * n_frames;
-    const uint64_t want = (n_tiles + FUSED_TPB / 32 - 1) / (FUSED_TPB / 32);
-    const unsigned grid = (unsigned)(want < (uint64_t)n_sm ? want : (uint64_t)n_sm);     // persistent: one CTA per SM
-    k_decode_fused<<<grid, FUSED_TPB, FUSED_SMEM, s>>>(j.d_blk_info + (size_t)j.stream_lo * nb, j.d_sym,
-                                                       j.d_seg_dc + j.sym_seg0, d_quant, (uint8_t*)d_out, nb, wb, W, n_frames);
+    const uint64_t n_items = (uint64_t)((nb + 31) / 32) * (d_gop_first ? n_gops : n_frames);
+    const uint64_t want = (n_items + FUSED_TPB / 32 - 1) / (FUSED_TPB / 32);
+    const unsigned grid = (unsigned)(want < (uint64_t)n_sm[dev] ? want : (uint64_t)n_sm[dev]);   // persistent: one CTA per SM
+    const uint2* bi = j.d_blk_info + (size_t)j.stream_lo * nb;
+    if (d_gop_first)
+        k_decode_fused<true><<<grid, FUSED_TPB, FUSED_SMEM, s>>>(bi, j.d_sym, j.d_seg_dc + j.sym_seg0, d_quant, (uint8_t*)d_out, nb, wb,
+                                                                 W, n_frames, d_gop_first, n_gops, (uint4*)d_state);
+    else
+        k_decode_fused<false><<<grid, FUSED_TPB, FUSED_SMEM, s>>>(bi, j.d_sym, j.d_seg_dc + j.sym_seg0, d_quant, (uint8_t*)d_out, nb, wb,
+                                                                  W, n_frames, nullptr, 0u, nullptr);
     return cudaGetLastError();
 }
 

@@ -108,8 +108,9 @@ int build_plan(const MpgIndex& idx, uint32_t first, uint32_t n, Plan& plan) {
 
 // Cut the plan into chunks of about K frames that start on I frames, and order each chunk's streams by
 // GOP depth (see Chunk in runtime.h).  For intra-only plans `ids` is simply 0, 1, 2, ...
-void make_chunks(const Plan& plan, uint32_t K, std::vector<Chunk>& chunks, std::vector<uint32_t>& ids) {
-    chunks.clear(); ids.clear();
+void make_chunks(const Plan& plan, uint32_t K, std::vector<Chunk>& chunks, std::vector<uint32_t>& ids,
+                 std::vector<uint32_t>& gops) {
+    chunks.clear(); ids.clear(); gops.clear();
     ids.reserve((size_t)plan.n * 3);
     K = std::max<uint32_t>(1, K);
     uint32_t f = 0;
@@ -132,6 +133,11 @@ void make_chunks(const Plan& plan, uint32_t K, std::vector<Chunk>& chunks, std::
                 if (depth[k - f] == l) for (uint32_t p = 0; p < 3; p++) ids.push_back(k * 3 + p);
         }
         ch.level_off.push_back((uint32_t)ids.size() - ch.ids_off);
+        ch.gop_off = (uint32_t)gops.size();
+        for (uint32_t k = f; k < e; k++)
+            if (depth[k - f] == 0) gops.push_back(k - f);
+        ch.n_gops = (uint32_t)gops.size() - ch.gop_off;
+        gops.push_back(e - f);
         chunks.push_back(std::move(ch));
         f = e;
     }
@@ -210,7 +216,7 @@ extern "C" void mjpeg423_b200_destroy(mjpeg423_b200_ctx* c) {
     cudaDeviceSynchronize();
     for (DevBuf* b : {&c->payload, &c->tables, &c->segs, &c->coef[0], &c->coef[1], &c->blkidx[0], &c->blkidx[1],
                       &c->samples, &c->stream_blocks, &c->misc, &c->ids, &c->in_ring[0], &c->in_ring[1], &c->out_ring[0],
-                      &c->out_ring[1]})
+                      &c->out_ring[1], &c->fstate[0], &c->fstate[1]})
         b->release();
     for (int i = 0; i < 2; i++) if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
     if (c->d_quant) cudaFree(c->d_quant);
@@ -297,8 +303,10 @@ int upload_tables(mjpeg423_b200_ctx* c, const Plan& plan, Tables& t, cudaStream_
 // (Re)build the chunk table for chunk size K and upload the level-ordered stream id list.
 int prepare_chunks(mjpeg423_b200_ctx* c, const Plan& plan, uint32_t K, cudaStream_t s) {
     if (c->chunk_K == K && !c->chunks.empty()) return MJPEG423_OK;
-    std::vector<uint32_t> ids;
-    make_chunks(plan, K, c->chunks, ids);
+    std::vector<uint32_t> ids, gops;
+    make_chunks(plan, K, c->chunks, ids, gops);
+    c->gops_base = ids.size();
+    ids.insert(ids.end(), gops.begin(), gops.end());                  // one upload: stream ids, then the GOP tables
     int rc = c->ids.reserve(ids.size() * 4 + 4);
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->ids.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, s));
@@ -320,7 +328,8 @@ uint32_t auto_chunk(const Plan& plan, uint64_t target_bytes, uint64_t bytes_per_
 }
 
 int decode_mode(const mjpeg423_b200_ctx* c, const Plan& plan) {
-    return plan.n_pframes ? std::max(1, c->staged) : c->staged;     // P frames need coefficient state in HBM
+    (void)plan;                  // (mode 0 decodes P frames too: k_decode_fused<true> keeps the state inside the warp)
+    return c->staged;
 }
 
 // Per-chunk scratch: block index (8 bytes per block) + symbol lists (SYM_STRIDE entries per segment) and,
@@ -389,7 +398,13 @@ int enqueue_chunk(mjpeg423_b200_ctx* c, const Plan& plan, const Tables& t, const
     if (prof) CU(cudaEventRecord(prof[3], s));
     c->stats.kernel_launches += 4;
     if (mode == 0) {
-        CU(launch_decode_fused(j, c->d_quant, d_out, f1 - f0, plan.W, plan.H, s));
+        const uint32_t* d_gops = nullptr;
+        if (plan.n_pframes) {                    // GOP-walking variant; its scratch belongs to this chunk buffer
+            int rc = c->fstate[buf].reserve(FUSED_STATE_BYTES);
+            if (rc) return rc;
+            d_gops = c->ids.as<uint32_t>() + c->gops_base + ch.gop_off;
+        }
+        CU(launch_decode_fused(j, c->d_quant, d_out, f1 - f0, plan.W, plan.H, d_gops, ch.n_gops, c->fstate[buf].p, s));
         c->stats.kernel_launches += 1;
         if (prof) for (int k = 4; k < N_PROF; k++) CU(cudaEventRecord(prof[k], s));
         return MJPEG423_OK;

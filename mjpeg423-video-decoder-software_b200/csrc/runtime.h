@@ -38,8 +38,13 @@ cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s);
 cudaError_t launch_entropy_index(const EntropyJob& j, cudaStream_t s);
 cudaError_t launch_decode_coef(const EntropyJob& j, const uint32_t* d_stream_ids, uint32_t n_ids, uint32_t nb,
                                const int16_t* d_quant, int16_t* d_coef, cudaStream_t s);
+// d_gop_first == nullptr: intra-only range.  Otherwise d_gop_first[0 .. n_gops] = chunk-relative first frames of the
+// range's GOPs (+ its end) and d_state = FUSED_STATE_BYTES of scratch that no other launch in flight uses.
+constexpr int FUSED_MAX_CTAS = 192;                                     // persistent grid: one CTA per SM, at most this many
+constexpr size_t FUSED_STATE_BYTES = (size_t)FUSED_MAX_CTAS * 18 * 3 * 8 * 32 * 16;   // 12 KB per warp
 cudaError_t launch_decode_fused(const EntropyJob& j, const int16_t* d_quant, void* d_out, uint32_t n_frames,
-                                uint32_t W, uint32_t H, cudaStream_t s);
+                                uint32_t W, uint32_t H, const uint32_t* d_gop_first, uint32_t n_gops, void* d_state,
+                                cudaStream_t s);
 cudaError_t launch_idct(const int16_t* d_coef, uint8_t* d_samples, size_t n_blocks, cudaStream_t s);
 cudaError_t launch_colour(const uint8_t* d_samples, void* d_out, uint32_t n_frames, uint32_t W, uint32_t H,
                           cudaStream_t s);
@@ -78,8 +83,11 @@ struct Chunk {
     uint32_t f0 = 0, f1 = 0;
     std::vector<uint32_t> level_off;             // size levels+1, offsets into the chunk's ids
     uint32_t ids_off = 0;
+    uint32_t gop_off = 0, n_gops = 0;            // gops[gop_off .. gop_off + n_gops]: chunk-relative first frame of every
+                                                 // GOP of the chunk, then f1 - f0 (what k_decode_fused<true> walks)
 };
-void make_chunks(const Plan& plan, uint32_t K, std::vector<Chunk>& chunks, std::vector<uint32_t>& ids);
+void make_chunks(const Plan& plan, uint32_t K, std::vector<Chunk>& chunks, std::vector<uint32_t>& ids,
+                 std::vector<uint32_t>& gops);
 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
@@ -109,8 +117,10 @@ struct mjpeg423_b200_ctx {
     mj::Plan plan;
     bool have_plan = false;
     DevBuf payload, tables, segs, coef[2], blkidx[2], samples, stream_blocks, misc, ids;
+    DevBuf fstate[2];           // k_decode_fused<true>: parked coefficient slots, one area per chunk buffer in flight
     std::vector<mj::Chunk> chunks;
     uint32_t chunk_K = 0;
+    size_t gops_base = 0;       // the GOP tables follow the stream ids in `ids` (in uint32 units)
     // staging for the host-buffer path
     DevBuf in_ring[2], out_ring[2];
     void* h_stage[2] = {nullptr, nullptr};
