@@ -66,6 +66,47 @@ __device__ __forceinline__ uint32_t parse_segment(const uint8_t* base, uint32_t 
     return pos;
 }
 
+// Number of leading all-zero 16-byte units at u (at most maxu are looked at).
+__device__ __forceinline__ uint32_t zero_units(const uint4* u, uint32_t maxu) {
+    for (uint32_t z = 0; z < maxu; z += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = z + j < maxu ? __ldg(u + z + j) : make_uint4(1u, 0u, 0u, 0u);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if ((v[j].x | v[j].y | v[j].z | v[j].w) != 0u) return z + j;
+    }
+    return maxu;
+}
+
+// parse_segment() with a shortcut for all-zero stretches: twelve zero bits are a whole block (DC size 0 + END,
+// what an unchanged block of a P frame is coded as), and a stream of them never self-synchronises -- every bit
+// position looks like a block start -- so on static pictures the chain kernel is what finds the block phase.  Blocks
+// that lie completely inside a run of zero 16-byte units are counted arithmetically (same positions and counts as
+// stepping through them); the parser takes over where the zeros end.
+__device__ __forceinline__ uint32_t parse_segment_z(const uint8_t* base, uint32_t entry, uint32_t seg_end,
+                                                    uint32_t ftotal, uint32_t& cnt) {
+    const uint32_t stop = min(seg_end, eos_stop(ftotal));
+    uint32_t pos = entry, k = 0;
+    if (pos < stop) {
+        const uintptr_t wbase = reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)3;      // f position 0
+        const uintptr_t a0 = (wbase + (pos >> 3)) & ~(uintptr_t)15;                     // unit that holds the entry bit
+        const uintptr_t a1 = wbase + ((min(seg_end, ftotal) + 7u) >> 3);                // scan no further than this
+        if (a1 > a0) {
+            const uint32_t z = zero_units(reinterpret_cast<const uint4*>(a0), (uint32_t)((a1 - a0 + 15) >> 4));
+            const uint64_t zend = (uint64_t)(a0 + 16u * (uintptr_t)z - wbase) * 8u;     // f position where the zeros end
+            if (zend >= (uint64_t)pos + MIN_BLOCK_BITS) {
+                k = min((stop - pos + MIN_BLOCK_BITS - 1u) / MIN_BLOCK_BITS, (uint32_t)((zend - pos) / MIN_BLOCK_BITS));
+                pos += k * MIN_BLOCK_BITS;
+            }
+        }
+    }
+    uint32_t c1 = 0;
+    const uint32_t x = parse_segment(base, pos, seg_end, ftotal, c1);
+    cnt = k + c1;
+    return x;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Speculative parse + merge.  A LANE parses a SUPER-segment: SUPER consecutive segments of one stream
 // (every stream's global segment range is padded to a multiple of SUPER, so super u = global segments
@@ -298,7 +339,7 @@ k_entropy_chain(const uint8_t* __restrict__ payload, const StreamDesc* __restric
             const uint32_t E = i ? v_exit[i - 1] : 0u;
             if (v_entry[i] != E) {
                 uint32_t cnt;
-                const uint32_t x = parse_segment(base, E + bias, (i + 1) * SEG_BITS + bias, ftotal, cnt) - bias;
+                const uint32_t x = parse_segment_z(base, E + bias, (i + 1) * SEG_BITS + bias, ftotal, cnt) - bias;
                 v_entry[i] = E;
                 v_exit[i] = x;
                 v_cnt[i] = cnt;

@@ -309,6 +309,35 @@ def test_pframe_streams(checker, dec, gop, chunk):
         dec.set_option(api.OPT_CHUNK_FRAMES, 0)
 
 
+@pytest.mark.parametrize("staged,chunk", [(0, 0), (0, 5), (1, 0)])
+def test_pframe_static_picture(checker, dec, staged, chunk):
+    """A static picture with a small moving patch: its P frames are long runs of unchanged blocks (twelve zero bits
+    each), which never self-synchronise -- the chain kernel finds their block phase (zero-run shortcut) -- and most
+    planes carry coefficient state through the GOP (k_decode_fused<true>: parked slots, DC and masks in registers)."""
+    W, H, n = 640, 480, 27
+    rng = np.random.default_rng(5)
+    fr = np.repeat(synth.synth_frame(W, H, 0, 24)[None], n, 0).copy()
+    for f in range(n):
+        x0 = (f * 24) % (W - 64)
+        fr[f, 200:264, x0:x0 + 64, :3] = rng.integers(0, 256, size=(64, 64, 3), dtype=np.uint8)
+    mpg = synth.encode_mpg(fr, gop=12)
+    assert mjpeg423_b200.probe(mpg).num_pframes >= 20
+    want = checker.decode_mpg(mpg)
+    dec.set_option(api.OPT_STAGED, staged)
+    dec.set_option(api.OPT_CHUNK_FRAMES, chunk)
+    try:
+        assert np.array_equal(dec.decode_frames(mpg), want)
+        dec.upload(mpg)
+        d_out = dec.device_alloc(want.nbytes)
+        dec.decode_resident(d_out)
+        assert np.array_equal(dec.to_host(d_out, want.nbytes).reshape(want.shape), want)
+        assert dec.stats()["fixups"] > 0          # the zero runs went through the chain kernel
+        dec.device_free(d_out)
+    finally:
+        dec.set_option(api.OPT_STAGED, 0)
+        dec.set_option(api.OPT_CHUNK_FRAMES, 0)
+
+
 def test_stage_entry_points(checker, dec):
     """Per-stage device entry points reproduce the reference's intermediate buffers."""
     W, H, n = 320, 240, 3
