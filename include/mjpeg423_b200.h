@@ -126,9 +126,9 @@ typedef struct {
 
 enum {
     MJPEG423_OPT_PROFILE      = 1,  /* 0/1: collect per-stage event times */
-    MJPEG423_OPT_STAGED       = 2,  /* 0: one fused decode kernel, bitstream -> BGRA (default; intra-only ranges);
-                                       1: coefficient planes in HBM + fused IDCT/colour kernel (used automatically
-                                          when the range holds P frames); 2: entropy, IDCT and colour kernels separate */
+    MJPEG423_OPT_STAGED       = 2,  /* 0: one fused decode kernel, bitstream -> BGRA (default; ranges with P frames
+                                          use its GOP-walking variant); 1: coefficient planes in HBM + fused
+                                          IDCT/colour kernel; 2: entropy, IDCT and colour kernels separate */
     MJPEG423_OPT_CHUNK_FRAMES = 3,  /* frames per pipeline chunk in the host-buffer path (0 = auto) */
     MJPEG423_OPT_VALIDATE     = 4   /* 0/1: check every stream decoded exactly num_blocks blocks (default 1) */
 };
