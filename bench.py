@@ -59,6 +59,34 @@ def measured_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+def bind_near_gpu(dev: int) -> dict | None:
+    """Multi-GPU boxes: run this rank on the CPUs next to its GPU (sysfs `local_cpulist` of the GPU's PCI function) so
+    that the pinned host buffers it allocates afterwards land on that NUMA node -- with eight ranks copying 50 GB/s
+    each, buffers on the far socket cap the box.  No effect where the GPU is local to every CPU (single-node VMs).
+    MJPEG423_BENCH_NO_BIND=1 turns it off."""
+    if os.environ.get("MJPEG423_BENCH_NO_BIND"):
+        return None
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        text = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        cpus = set()
+        for part in text.split(","):
+            if part:
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        have = os.sched_getaffinity(0)
+        cpus &= have
+        if not cpus or cpus == have:
+            return {"numa_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:           # no sysfs / old torch: run unbound
+        return {"bound": False, "why": str(e)[:80]}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons of one GPU, sampled every 50 ms.  The sampler is started EARLY (nvidia-smi
     needs about a second to enumerate an 8-GPU box) and reads its lines with their arrival time; begin()/end() mark the
@@ -399,6 +427,7 @@ def main():
         my_frames = hi - lo
     else:
         my_frames = frames
+    binding = bind_near_gpu(local_rank) if world > 1 else None
     cores = os.cpu_count() or 1
     mpg, uniq, q = make_stream(args.workload, my_frames, max(1, cores // world))
     frame_bytes = W * H * 4
@@ -585,6 +614,7 @@ def main():
                        "l2": "inputs larger than L2 (bitstream %.0f MB, output %.1f GB per GPU per step)" %
                              (payload_bytes / 1e6, my_frames * frame_bytes / 1e9),
                        "parallelism": f"frame-range x{world}, no collective", "timing": "cuda events, max over ranks",
+                       "cpu_binding": binding,
                        "wall_ms_per_step": wall_ms_max / args.steps, "verified": verified},
             "clocks": clocks,
             "e2e": {"value": total_e2e_frames * e2e_steps / e2e_s_max, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_bytes),
