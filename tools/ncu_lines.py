@@ -48,6 +48,8 @@ base, tot, totie, recs = None, 0, 0, []
 for r in rows[h + 1:]:
     if len(r) <= S or not r[A]:
         continue
+    if r[A] == "Address":          # the regex matched another launch: keep the first one
+        break
     a = int(r[A], 16) if r[A].startswith("0x") else int(r[A])
     base = a if base is None else base
     s, ie = int(r[S] or 0), int(r[IE] or 0)
