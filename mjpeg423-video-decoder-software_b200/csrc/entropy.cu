@@ -212,7 +212,8 @@ __device__ __forceinline__ void resolve_super(SyncShared& sh, const uint8_t* bas
             }
         }
     }
-    while (__any_sync(FULL_MASK, next_stop != NO_WORK)) {
+    // (four steps per look at the loop condition: a lane that is done is parked, extra steps change nothing)
+    auto one_step = [&]() {
         Parser::Sym y;
         const bool end = ps.step<false, FOLD>(y);
         cnt += end ? 1u : 0u;
@@ -234,6 +235,12 @@ __device__ __forceinline__ void resolve_super(SyncShared& sh, const uint8_t* bas
             if (done) { ps.park(); next_stop = NO_WORK; }
             else next_stop = min(s0 + ck_bnd(inext), fstop_eos);
         }
+    };
+    while (__any_sync(FULL_MASK, next_stop != NO_WORK)) {
+        one_step();
+        one_step();
+        one_step();
+        one_step();
     }
 }
 
@@ -261,7 +268,8 @@ k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
 #pragma unroll
             for (int i = 0; i < NCK; i++) sh.cp[i][t] = 0u;
         }
-        while (__any_sync(FULL_MASK, next_stop != NO_WORK)) {
+        // (four steps per look at the loop condition: a lane that is done is parked, extra steps change nothing)
+        auto one_step = [&]() {
             Parser::Sym y;
             const bool end = ps.step<false, FOLD>(y);
             cnt += end ? 1u : 0u;
@@ -277,6 +285,12 @@ k_entropy_sync(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
                     next_stop = min(s0 + ck_bnd(j), fstop_eos);
                 }
             }
+        };
+        while (__any_sync(FULL_MASK, next_stop != NO_WORK)) {
+            one_step();
+            one_step();
+            one_step();
+            one_step();
         }
     }
     __syncthreads();
@@ -447,7 +461,8 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
         }
     };
     grab((uint32_t)t);
-    while (__any_sync(FULL_MASK, cnt != 0u)) {
+    // (four steps per look at the loop condition: a lane that is done is parked, extra steps change nothing)
+    auto one_step = [&]() {
         Parser::Sym y;
         const bool end = ps.step<true, FOLD>(y);
         if (y.dc) { cur = pframe ? y.e : cur + y.e; o_blk = o; }
@@ -479,6 +494,12 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
                 grab(atomicAdd(&s_next, 1u));
             }
         }
+    };
+    while (__any_sync(FULL_MASK, cnt != 0u)) {
+        one_step();
+        one_step();
+        one_step();
+        one_step();
     }
     {   // statistics: list entries written by this launch (one atomic per warp)
 #pragma unroll
