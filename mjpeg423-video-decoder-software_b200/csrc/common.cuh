@@ -80,7 +80,8 @@ struct Parser {
     uint32_t w0, w1, w2;   // current word, look-ahead word, word in flight; MSB first
     uint32_t fpos;         // f position of the next symbol
     uint32_t flim;         // a block is ended at or after this f position (see above)
-    uint32_t idx;          // zig-zag index of the next AC coefficient
+    uint32_t idx;          // zig-zag index of the next AC coefficient << 24 (the add wraps at 8 bits like the reference's
+                           // uint8_t index, and "coefficient 63" is one unsigned compare)
     uint32_t nh;           // minus the header length of the next symbol: -4 = DC (a block start), -8 = AC
     uint32_t rmask;        // 32 while live; 0 = PARKED: the window is never refilled again (see park())
 
@@ -94,7 +95,7 @@ struct Parser {
         wp = w + 3;
         fpos = fbits;
         flim = min(job_end + RUNAWAY_BITS, ftotal);
-        idx = 1;
+        idx = 1u << 24;
         nh = (uint32_t)-4;
         rmask = 32u;
     }
@@ -104,14 +105,14 @@ struct Parser {
     // and the pass ignores what it returns.
     __device__ __forceinline__ void park() { rmask = 0u; w0 = 0u; w1 = 0u; }
     __device__ __forceinline__ void init_parked() {
-        wp = nullptr; w0 = w1 = w2 = 0u; fpos = 0u; flim = 0u; idx = 1u; nh = (uint32_t)-4; rmask = 0u;
+        wp = nullptr; w0 = w1 = w2 = 0u; fpos = 0u; flim = 0u; idx = 1u << 24; nh = (uint32_t)-4; rmask = 0u;
     }
 
     // What the last step() consumed.
     struct Sym {
         bool dc;           // it was the block's DC symbol
         bool coded;        // it was a non-zero AC coefficient ...
-        uint32_t at;       // ... at this zig-zag index (may be >= 64 on non-conforming input: ignore then)
+        uint32_t at;       // ... at this zig-zag index << 24 (may be >= 64 << 24 on non-conforming input: ignore then)
         int e;             // WANT_E only: amplitude of the DC / coded AC coefficient (HUFF_EXTEND, :204); 0 for a
                            // size-0 DC symbol, unspecified for END / ZRL
     };
@@ -139,8 +140,8 @@ struct Parser {
         }
         const bool szd = size != 0u || dc;
         const bool coded = size != 0u && !dc;                           // a non-zero AC coefficient
-        const uint32_t at = (idx + (szd ? run : 16u)) & 255u;           // DC: idx (1); ZRL: idx + 16; coefficient: its index
-        const bool end0 = (!szd && run != 15u) || (coded && at >= 63u); // END / coefficient 63
+        const uint32_t at = idx + ((szd ? run : 16u) << 24);            // DC: idx (1); ZRL: idx + 16; coefficient: its index
+        const bool end0 = (!szd && run != 15u) || (coded && at >= (63u << 24));   // END / coefficient 63
         const bool end_next = FOLD_END && !end0 && ((t << len) >> 24) == 0u;   // ... or an END right behind this symbol
         const uint32_t fnew = fpos + len + (end_next ? 8u : 0u);        // <= 31 bits: at most one word crossing
         if ((fpos ^ fnew) & rmask) {                                    // crossed into w1: fetch the word after w2
@@ -150,7 +151,7 @@ struct Parser {
             wp++;
         }
         const bool end = end0 || end_next || fnew >= flim;              // ... or the guard
-        idx = end ? 1u : at + (coded ? 1u : 0u);
+        idx = end ? (1u << 24) : at + (coded ? (1u << 24) : 0u);
         nh = end ? (uint32_t)-4 : (uint32_t)-8;
         fpos = fnew;
         sym.dc = dc;

@@ -466,10 +466,10 @@ k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restric
         Parser::Sym y;
         const bool end = ps.step<true, FOLD>(y);
         if (y.dc) { cur = pframe ? y.e : cur + y.e; o_blk = o; }
-        if (y.coded && y.at < 64u) {                     // (a parked lane never sees a coded symbol)
+        if (y.coded && y.at < (64u << 24)) {             // (a parked lane never sees a coded symbol)
 #pragma unroll
             for (int i = 0; i < 7; i++) q[i] = q[i + 1];
-            q[7] = y.at | tag | ((uint32_t)y.e << 16);
+            q[7] = (y.at >> 24) | tag | ((uint32_t)y.e << 16);
             o++;
             if ((o & 7u) == 0u && o <= o_end) st_global_v8(sym + o - 8, q);   // never overflows on conforming streams
         }
