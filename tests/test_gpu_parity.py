@@ -442,3 +442,39 @@ def test_garbage_streams_are_survived(checker):
     stream = _encode_levels(wire)
     assert np.array_equal(mjpeg423_b200.lossless_decode(200, stream, None, api.YQUANT, 0),
                           checker.lossless_decode(200, stream, api.YQUANT, 0))
+
+
+@pytest.mark.parametrize("staged", [0, 1])
+def test_garbage_containers_are_survived(checker, dec, staged):
+    """Well-formed containers whose plane streams are garbage (random bytes, zeros, all-ones; I and P frame types):
+    the whole pipeline -- with P frames the GOP-walking fused kernel and the chain kernel's zero-run shortcut -- must
+    neither fault nor hang, and must decode a good stream afterwards.  (Nothing is compared: the reference has
+    undefined behaviour on such input.)"""
+    W, H, n = 160, 96, 7
+    rng = np.random.default_rng(17)
+    fr = np.repeat(synth.synth_frame(W, H, 0, 24)[None], n, 0).copy()
+    for f in range(n):
+        fr[f, 8:40, 16 * f:16 * f + 32, :3] = rng.integers(0, 256, size=(32, 32, 3), dtype=np.uint8)
+    good = synth.encode_mpg(fr, gop=3)
+    assert mjpeg423_b200.probe(good).num_pframes >= 3
+    want = checker.decode_mpg(good)
+    dec.set_option(api.OPT_STAGED, staged)
+    dec.set_option(api.OPT_VALIDATE, 0)
+    try:
+        for fill in ("random", "zeros", "ones"):
+            bad = good.copy()
+            off = 20
+            for f in range(n):
+                fsz = int(bad[off:off + 4].view("<u4")[0])
+                body = bad[off + 16:off + fsz]
+                body[:] = {"random": rng.integers(0, 256, size=body.size, dtype=np.uint8), "zeros": 0, "ones": 255}[fill]
+                off += fsz
+            try:
+                out = dec.decode_frames(bad)
+                assert out.shape == want.shape
+            except RuntimeError:
+                pass                                    # a reported stream error is fine as well
+            assert np.array_equal(dec.decode_frames(good), want)
+    finally:
+        dec.set_option(api.OPT_STAGED, 0)
+        dec.set_option(api.OPT_VALIDATE, 1)
