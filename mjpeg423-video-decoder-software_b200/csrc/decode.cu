@@ -249,6 +249,14 @@ k_decode_fused(const uint2* __restrict__ blk_info,
             } else {
                 if (lane < n1 + n2) npreC[p - 1] = __ldg(sym + (r0 + lane + (lane < n1 ? 0u : d2)));
             }
+            {   // what does not fit the registers (busy tiles) is pulled into L2, one 128-byte line per lane and run:
+                // the staging copy of the next tile then pays an L2 hit instead of a DRAM access
+                const uint32_t pre = p == 0 ? 32u * PRE_Y : 32u;
+                const uint32_t u1 = min(n1, pre), u2 = min(pre - u1, n2);
+                const uint32_t q1 = r0 + u1 + lane * 32u, q2 = s0 + u2 + lane * 32u;
+                if (q1 < r0 + n1) asm volatile("prefetch.global.L2 [%0];" ::"l"(sym + q1));
+                if (q2 < s0 + n2) asm volatile("prefetch.global.L2 [%0];" ::"l"(sym + q2));
+            }
         }
     };
     // Staging area of the warp for list remainders: the lower half of its workspace granules (dead while a plane
