@@ -9,8 +9,8 @@
 //                   with the previous frame's coefficients for P frames, :90-92,121-123), dequantising
 //                   as it scatters zig-zag -> natural order (:122-126); the CTA then stores its 128
 //                   consecutive blocks as one contiguous, fully coalesced 16 KB run.
-//   k_decode_fused  the whole reference loop body, LIB/decoder/mjpeg423_decoder.c:110-124, for intra
-//                   frames: a warp takes 32 block positions, reads the lists of their Y, Cb and Cr blocks with
+//   k_decode_fused  the whole reference loop body, LIB/decoder/mjpeg423_decoder.c:110-124 (<false>: intra-only
+//                   ranges; <true>: ranges with P frames, a GOP at a time): a warp takes 32 block positions, reads the lists of their Y, Cb and Cr blocks with
 //                   coalesced loads and scatters them into the owners' shared-memory slots, every thread then runs
 //                   the three IDCTs of its position through shared memory (idct.c:22-181) and writes the 8x8
 //                   BGRA pixels (ycbcr_to_rgb.c:26-49).  Coefficients and samples never touch HBM:
@@ -133,7 +133,6 @@ k_decode_coef(const StreamDesc* __restrict__ streams, const uint32_t* __restrict
 constexpr int FUSED_TPB = 576;                                   // 18 warps x 384 B/thread = 216 KB of the SM's 227 KB
 constexpr int FUSED_SMEM = FUSED_TPB * (256 + 128) + 2 * 64 * 8 + 16;     // + the CTA's tile counter
 
-//
 // PF = true is the variant for ranges that hold P frames (LIB/decoder/lossless_decode.c:90-92,121-123: every decoded
 // value is ADDED to the previous frame's coefficient).  A work item is then (tile, GOP): the warp walks the GOP's frames
 // in order for one tile, so the inter-frame state never leaves the warp: the DC values and the accumulated column
