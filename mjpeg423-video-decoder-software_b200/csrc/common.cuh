@@ -288,6 +288,14 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
                  : "memory");
 }
 
+// 256-bit global load (coherent: the data may have been written by this thread earlier in the kernel).
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p)
+                 : "memory");
+}
+
 // ---- packed colour conversion: LIB/decoder/ycbcr_to_rgb.c:26-49 ---------------------------------------------
 // R = (Y << 14) + 22970 (Cr - 128), G = (Y << 14) - 5638 (Cb - 128) - 11700 (Cr - 128), B = (Y << 14) + 29032 (Cb - 128)
 // (:33-37), each through NORMALIZE_RGB (:19): negative -> 0, else >> 14, capped at 255.  Pixel word = B | G << 8 |

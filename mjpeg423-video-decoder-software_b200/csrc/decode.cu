@@ -278,6 +278,22 @@ k_decode_fused(const uint2* __restrict__ blk_info,
     uint32_t mY = 1u, mB = 1u, mR = 1u;
     uint4* my_state = PF ? state + ((size_t)(blockIdx.x * (FUSED_TPB / 32) + (t >> 5)) * 3u * 8u) * 32u + lane : nullptr;
 
+    // The pipeline step: index entries of the next position become current, its list heads are requested, the
+    // index entries of the position after it are requested.
+    auto advance = [&](uint32_t raw2) {
+        // (The rotation is spelled as opaque moves in front of the loads: otherwise the loads land in temporaries
+        // that are copied into the loop-carried registers at once, i.e. waited for right here.)
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            asm volatile("mov.b32 %0, %1;" : "=r"(infoA[q].x) : "r"(infoB[q].x));
+            asm volatile("mov.b32 %0, %1;" : "=r"(infoA[q].y) : "r"(infoB[q].y));
+        }
+        prefetch_lists();
+        if (nn_first) nn = item_pos(raw2);
+        else { nn.f = nxt.f + 1u; nn.tb = nxt.tb; nn.fend = nxt.fend; }
+        load_info(nn, infoB);
+    };
+
     for (; cur.f < n_frames; cur = nxt, nxt = nn, cur_first = nxt_first, nxt_first = nn_first) {
         nn_first = !(PF && nxt.f + 1u < nxt.fend);
         const uint32_t raw2 = nn_first ? take() : 0u;                     // the item after the next position's
@@ -296,6 +312,26 @@ k_decode_fused(const uint2* __restrict__ blk_info,
         for (int i = 0; i < PRE_Y; i++) preY[i] = npreY[i];
         preC[0] = npreC[0]; preC[1] = npreC[1];
 
+        if (PF && !cur_first) {
+            // P frame whose 32 positions are all unchanged (no entry, zero DC deltas, in all three planes -- what a
+            // static background is coded as): the pixels are the previous frame's, which this lane wrote itself.
+            bool same = true;
+#pragma unroll
+            for (int p = 0; p < 3; p++) same = same && lx[p] == lxe[p] && (meta[p] & 0xFFFFu) == 0u;
+            if (__all_sync(FULL_MASK, same)) {
+                if (live) {
+                    const uint8_t* prev = dst - (size_t)nb * 256;
+#pragma unroll 4
+                    for (int r = 0; r < 8; r++) {
+                        uint32_t v[8];
+                        ld_global_v8(prev + (size_t)r * W * 4, v);
+                        st_global_v8(dst + (size_t)r * W * 4, v);
+                    }
+                }
+                advance(raw2);
+                continue;
+            }
+        }
         bool cb_flat = false;                                            // warp-uniform: every Cb block of the tile is DC-only;
         uint32_t cb_s8 = 0;                                              // its sample then waits here, not in the stash
 #pragma unroll 1
@@ -434,19 +470,7 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                 }
             }
             if (PF) { if (p == 0) mY = m_all; else if (p == 1) mB = m_all; else mR = m_all; }
-            if (p == 0) {                                                 // behind the luminance scatter: the pipeline advances
-                // (The rotation is spelled as opaque moves in front of the loads: otherwise the loads land in temporaries
-                // that are copied into the loop-carried registers at once, i.e. waited for right here.)
-#pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    asm volatile("mov.b32 %0, %1;" : "=r"(infoA[q].x) : "r"(infoB[q].x));
-                    asm volatile("mov.b32 %0, %1;" : "=r"(infoA[q].y) : "r"(infoB[q].y));
-                }
-                prefetch_lists();
-                if (nn_first) nn = item_pos(raw2);
-                else { nn.f = nxt.f + 1u; nn.tb = nxt.tb; nn.fend = nxt.fend; }
-                load_info(nn, infoB);
-            }
+            if (p == 0) advance(raw2);                                    // behind the luminance scatter: the pipeline advances
             const uint32_t acm = m_all >> 8, anym = m_all & 0xFFu;
 
             if (((anym & 0xFEu) | (acm & 1u)) == 0) { dc_only_plane(); continue; }   // nothing outside the DC position
