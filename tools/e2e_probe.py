@@ -1,5 +1,8 @@
+"""End-to-end call (pinned host .mpg -> pinned host frames) against the pipeline chunk size: wall and event time per
+call.  python tools/e2e_probe.py   (compare with tools/pcie_probe.py on the same box)"""
 import sys, time, numpy as np
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mjpeg423_b200
 from mjpeg423_b200 import api, synth
 W,H=1920,1080
