@@ -1,4 +1,5 @@
-"""P-frame stream decode timing: encode procedural 1080p frames with the GPU encoder (GOP 24), decode resident."""
+"""P-frame stream decode timing: encode procedural 1080p frames with the GPU encoder (GOP 24), decode resident, verify.
+    python tools/pframe_run.py [frames] [--no-verify]"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -24,5 +25,11 @@ d_out = dec.device_alloc(n * W * H * 4)
 for _ in range(3):
     dec.decode_resident(d_out)
 st = dec.stats()
+if "--no-verify" not in sys.argv:                      # every frame against the reference's own decoder (64-bit checksums)
+    from oracle import oracle
+    want = api.frame_hash_host(oracle.best().decode_mpg(mpg, nthreads=os.cpu_count() or 1))
+    got = dec.hash_frames(d_out, W * H * 4, n)
+    assert np.array_equal(got, want), "P-frame decode differs from the oracle"
+    print("verified", n, "frames against the oracle")
 print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items()})
 print("fps", n / st["total_ms"] * 1e3)
