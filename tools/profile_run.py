@@ -34,5 +34,12 @@ d_out = dec.device_alloc(a.frames * W * H * 4)
 for _ in range(a.passes):
     dec.decode_resident(d_out)
 print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in dec.stats().items()})
+if a.profile:                      # the pipelined total (chunks overlapped on two streams), median of 5
+    dec.set_option(api.OPT_PROFILE, 0)
+    ms = []
+    for _ in range(7):
+        dec.decode_resident(d_out)
+        ms.append(dec.stats()["total_ms"])
+    print("pipelined_ms", round(sorted(ms)[3], 3), "chunks", len(ms) and dec.stats().get("kernel_launches"))
 dec.device_free(d_out)
 dec.close()
