@@ -483,7 +483,7 @@ k_decode_fused(const uint2* __restrict__ blk_info,
             // ---- pass 1: columns, two at a time (idct.c:41-109) --------------------------------------------------
             const bool high_half = (anym & 0xF0u) != 0;
             const int npair = high_half ? 4 : 2;
-#pragma unroll 1
+#pragma unroll 2                 // (two pairs = four butterflies in flight; within a pair of iterations no store hits a later load)
             for (int cp = 0; cp < npair; cp++) {
                 const uint4 c0 = *reinterpret_cast<const uint4*>(my_coef + (2 * cp) * (FUSED_TPB * 16));
                 const uint4 c1 = *reinterpret_cast<const uint4*>(my_coef + (2 * cp + 1) * (FUSED_TPB * 16));
