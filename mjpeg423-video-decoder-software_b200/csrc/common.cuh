@@ -23,14 +23,35 @@ constexpr int ENT_TPB = 128;                   // threads per CTA in the entropy
 constexpr int MIN_BLOCK_BITS = 12;             // DC size 0 + END
 constexpr uint32_t RUNAWAY_BITS = 8192;        // parse guard for non-conforming / speculative garbage
 constexpr uint32_t MAX_STREAM_BYTES = 1u << 28; // bit positions are 32-bit
-// Symbol list: the index pass writes every coded AC coefficient of a segment's blocks as one 32-bit entry
-// (zig-zag index | amplitude << 16) into a fixed-stride region.  A segment owns at most SEG_BITS/9 coded
-// symbols (>= 9 bits each) that start inside it plus the rest of its last block (<= 63 AC coefficients).
-constexpr uint32_t SYM_STRIDE = (SEG_BYTES * 8 / 9 + 63 + 7) / 8 * 8;   // entries per segment, a multiple of 8
-// Block index entry (uint2): .x = position of the block's first list entry -- always inside its segment's
-// region, so .x / SYM_STRIDE names the segment (whose DC predictor the decode kernels add) -- or BLK_NO_SEG
-// for a block the stream does not hold; .y = segment-relative DC level | list entries << 16.
-constexpr uint32_t BLK_NO_SEG = 0xFFFFFFFFu;
+constexpr uint32_t MAX_PLANE_BLOCKS = 1u << 24; // blocks per plane (W/8 * H/8): 32768 x 32768 pixels
+// Record lists: the emit pass (k_entropy_emit) writes ONE 32-bit record per symbol step of a segment's blocks into a
+// fixed-stride region (the steps of the lanes of a warp are synchronous, so the record position is the step count:
+// no compaction, no per-lane queue):
+//     bits 0..7  zig-zag index of a coded AC coefficient (1..63); 0 in a DC record; 255 = the step carried no
+//                coefficient (ZRL, a stand-alone END); other values >= 64 = non-conforming input, ignored
+//     bit 8      set for a block's DC symbol
+//     bits 16..31  AC: amplitude (HUFF_EXTEND, LIB/decoder/lossless_decode.c:204)
+//                  DC: I frames: the int16 running sum `cur` (:73,94) restarted at 0 at the segment's first block;
+//                      P frames: the DC delta itself (:91)
+// Every block starts with its DC record, so the consumers find block boundaries by counting bit 8.
+// A conforming segment takes at most SEG_BITS / 6 steps that start inside it (DC size 0 + stand-alone END = two
+// steps per 12 bits) plus the rest of its last block (<= 68 steps): 751.
+constexpr uint32_t REC_STRIDE = 768;            // records per segment region, a multiple of 8 (32-byte sector stores)
+constexpr uint32_t REC_DC = 0x100u, REC_NONE = 0xFFu;
+// The record carries a coefficient: a DC record, or a coded AC coefficient with a conforming index.
+__device__ __forceinline__ bool rec_valid(uint32_t e) { return (e & 0xFFu) < 64u; }
+// blkrec: per segment, the record offset (u16) of every block's DC record, then the segment's record count;
+// <= SEG_BITS / MIN_BLOCK_BITS + 1 blocks.
+constexpr uint32_t BLK_STRIDE = 352;
+// Tile descriptor (k_entropy_tiles): where the records of 32 consecutive blocks of one plane lie.  They form one
+// run per bitstream segment the tile touches ("run" = a contiguous range of one segment's region).
+//   fast.x = record index of the tile's first record (the DC record of block 32 T), fast.y = first record of the
+//   second run | TILE_MORE when the tile has more than two runs, fast.z = records of the first run | of the second
+//   << 16, fast.w = DC predictor entering the first run's segment | the second's << 16 (I frames; 0 for P frames);
+//   slow.x = global segment of the second run, slow.y = number of runs, slow.z = records of the LAST run that belong
+//   to the tile (the runs between the second and the last are whole segments).
+struct TileDesc { uint4 fast, slow; };
+constexpr uint32_t TILE_MORE = 0x80000000u;
 
 // One plane bitstream of one frame (built by the host from the 16-byte frame headers,
 // LIB/decoder/mjpeg423_decoder.c:94-107).
@@ -66,18 +87,72 @@ struct StreamDesc {
 // (w0 = current, w1 = next).  Positions are counted from the ALIGNED word that holds the stream's first
 // byte ("f" positions = stream bit position + bias, bias = 8 * (address & 3)), so the offset into w0 is
 // simply fpos & 31: the next 32 stream bits are ONE funnel shift (which takes its amount mod 32) and a
-// word crossing is bit 5 of fpos flipping.  A third word w2 is in flight behind them: the funnel shift reads
-// w1 in EVERY step, so a word loaded straight into w1 would be waited for one step later; loaded into w2 it
-// is not touched until the next crossing (3-4 symbols), which hides an L2 round trip.  The payload buffer
-// is padded: reads up to 16 bytes past any stream end are in bounds.
+// word crossing is bit 5 of fpos flipping.  The words behind the window come from a Feed (below).  The payload
+// buffer is padded by PAYLOAD_PAD bytes: reads a few words past any stream end are in bounds.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t stream_bias(const uint8_t* base) {
     return (uint32_t)(reinterpret_cast<uintptr_t>(base) & 3u) * 8u;
 }
 
-struct Parser {
+// Where the parser's bitstream words come from.  take() is called when the window crosses into its second word: it
+// returns the next window word (big-endian) and requests the one after the word in flight.
+//
+// FeedReg: the word in flight lives in a register (w2), requested with a plain load.  Simple, but the hardware
+// tracks register loads per warp: the PRMT that consumes w2 at a crossing waits for the load ANOTHER lane issued one
+// step earlier, so a warp makes one step per L2 round trip unless other warps cover it (fine for short or rare
+// passes: the chain kernel).
+struct FeedReg {
     const uint32_t* wp;    // next aligned word to fetch
-    uint32_t w0, w1, w2;   // current word, look-ahead word, word in flight; MSB first
+    uint32_t w2;           // word in flight (raw: byte-swapped when it moves into the window)
+    __device__ __forceinline__ void start(const uint32_t* w) { w2 = __ldg(w + 2); wp = w + 3; }
+    __device__ __forceinline__ void init_parked() { wp = nullptr; w2 = 0u; }
+    __device__ __forceinline__ uint32_t take() {
+        const uint32_t r = __byte_perm(w2, 0, 0x0123);
+        w2 = __ldg(wp);
+        wp++;
+        return r;
+    }
+};
+// FeedRing<T>: the words in flight live in a per-lane ring of RING_WORDS words in shared memory (slot s of thread t at
+// ring + (s * T + t) * 4: conflict-free), filled with cp.async SIXTEEN words ahead of the one the window takes next.
+// cp.async has no destination register, so nothing waits for a request until the pass says so: ONE
+// cp.async.wait_all per group of 8 steps (a lane crosses at most 8 words in 8 steps, and a word is requested at
+// least 9 crossings before it is read, so a wait lies between every request and its read).  The ring of a CTA must
+// be aligned to its size (the slot address wraps with one LOP3).  Reads run up to 19 words past the window: the
+// payload buffer is padded by PAYLOAD_PAD bytes.
+constexpr int RING_WORDS = 32;
+constexpr size_t PAYLOAD_PAD = 128;
+template <int T>
+struct FeedRing {
+    static constexpr uint32_t STRIDE = T * 4u, BYTES = RING_WORDS * STRIDE;
+    uint32_t ra;           // shared address of the slot the next take() reads
+    const uint32_t* gp;    // global word the next take() requests (it goes to slot + 16)
+    uint32_t w2;           // look-ahead word (raw), read from the ring at the previous crossing
+    // ring_t = shared address of slot 0 of this thread
+    __device__ __forceinline__ void start(const uint32_t* w, uint32_t ring_t) {
+        w2 = __ldg(w + 2);
+        ra = ring_t;
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_t + k * STRIDE), "l"(w + 3 + k) : "memory");
+        gp = w + 19;
+    }
+    __device__ __forceinline__ void init_parked(uint32_t ring_t) { ra = ring_t; gp = nullptr; w2 = 0u; }
+    __device__ __forceinline__ uint32_t take() {
+        const uint32_t r = __byte_perm(w2, 0, 0x0123);
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(ra) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ra ^ (16u * STRIDE)), "l"(gp) : "memory");
+        gp++;
+        ra = (ra & ~(BYTES - 1u)) | ((ra + STRIDE) & (BYTES - 1u));
+        return r;
+    }
+    static __device__ __forceinline__ void wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+};
+
+template <class Feed>
+struct ParserT {
+    Feed fd;
+    uint32_t w0, w1;       // current word, look-ahead word; MSB first
     uint32_t fpos;         // f position of the next symbol
     uint32_t flim;         // a block is ended at or after this f position (see above)
     uint32_t idx;          // zig-zag index of the next AC coefficient << 24 (the add wraps at 8 bits like the reference's
@@ -87,12 +162,12 @@ struct Parser {
 
     // fbits = f position to start at (a block start), job_end = f position where the caller's job ends (it stops at
     // the first block start at or after it), ftotal = f position of the end of the stream.
-    __device__ __forceinline__ void start(const uint8_t* base, uint32_t fbits, uint32_t job_end, uint32_t ftotal) {
+    template <class... A>
+    __device__ __forceinline__ void start(const uint8_t* base, uint32_t fbits, uint32_t job_end, uint32_t ftotal, A... feed_args) {
         const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)3) + (fbits >> 5);
         w0 = __byte_perm(__ldg(w), 0, 0x0123);
         w1 = __byte_perm(__ldg(w + 1), 0, 0x0123);
-        w2 = __ldg(w + 2);                               // kept raw: byte-swapped when it moves into w1
-        wp = w + 3;
+        fd.start(w, feed_args...);
         fpos = fbits;
         flim = min(job_end + RUNAWAY_BITS, ftotal);
         idx = 1u << 24;
@@ -104,8 +179,10 @@ struct Parser {
     // window (DC size 0 / END symbols: no coefficient, 4 or 8 bits each) without ever touching memory again,
     // and the pass ignores what it returns.
     __device__ __forceinline__ void park() { rmask = 0u; w0 = 0u; w1 = 0u; }
-    __device__ __forceinline__ void init_parked() {
-        wp = nullptr; w0 = w1 = w2 = 0u; fpos = 0u; flim = 0u; idx = 1u << 24; nh = (uint32_t)-4; rmask = 0u;
+    template <class... A>
+    __device__ __forceinline__ void init_parked(A... feed_args) {
+        fd.init_parked(feed_args...);
+        w0 = w1 = 0u; fpos = 0u; flim = 0u; idx = 1u << 24; nh = (uint32_t)-4; rmask = 0u;
     }
 
     // What the last step() consumed.
@@ -144,11 +221,9 @@ struct Parser {
         const bool end0 = (!szd && run != 15u) || (coded && at >= (63u << 24));   // END / coefficient 63
         const bool end_next = FOLD_END && !end0 && ((t << len) >> 24) == 0u;   // ... or an END right behind this symbol
         const uint32_t fnew = fpos + len + (end_next ? 8u : 0u);        // <= 31 bits: at most one word crossing
-        if ((fpos ^ fnew) & rmask) {                                    // crossed into w1: fetch the word after w2
+        if ((fpos ^ fnew) & rmask) {                                    // crossed into w1: take the next word
             w0 = w1;
-            w1 = __byte_perm(w2, 0, 0x0123);
-            w2 = __ldg(wp);
-            wp++;
+            w1 = fd.take();
         }
         const bool end = end0 || end_next || fnew >= flim;              // ... or the guard
         idx = end ? (1u << 24) : at + (coded ? (1u << 24) : 0u);
@@ -160,6 +235,7 @@ struct Parser {
         return end;
     }
 };
+using Parser = ParserT<FeedReg>;
 
 constexpr uint32_t FULL_MASK = 0xFFFFFFFFu;
 
@@ -283,7 +359,7 @@ __device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_syn
 
 // 256-bit global store (sm_100+): one full 32-byte sector per lane.
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
                  "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }

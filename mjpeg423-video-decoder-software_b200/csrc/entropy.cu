@@ -394,142 +394,177 @@ k_entropy_chain(const uint8_t* __restrict__ payload, const StreamDesc* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// Block index + symbol lists.  Walking its blocks from the exact state, a segment's thread writes
-//   sym[seg * SYM_STRIDE + ...]  one entry per coded AC coefficient: zig-zag index | (block index & 31) << 6 |
-//                                amplitude << 16 (the block bits name the lane that owns the block in
-//                                k_decode_fused's warp tiles of 32 consecutive blocks)
-//   blk_info[block].x            index of the block's first entry in sym[] (always inside the segment's region,
-//                                so x / SYM_STRIDE identifies the segment), or BLK_NO_SEG for a block the stream
-//                                does not hold
-//   blk_info[block].y            DC level relative to the segment's entry (I frames: the int16 running sum `cur`
-//                                of LIB/decoder/lossless_decode.c:73,94 restarted at 0; P frames: the DC delta
-//                                itself, :91) | entries << 16
-//   seg_dc[segment]              I frames: sum of the segment's DC deltas (mod 2^16); P frames: 0
-// After this pass no kernel touches the bitstream again: the block-parallel decode kernels (decode.cu)
-// read the lists with independent, look-ahead loads instead of a bit-serial dependent chain.
+// Record lists.  Walking its blocks from the exact state, a segment's lane writes
+//   rec[seg * REC_STRIDE + step]     one record per symbol step (layout: common.cuh); the lanes of a warp step in
+//                                    lock-step from step 0, so the record position is warp-uniform and eight
+//                                    consecutive records leave as ONE 32-byte sector store, straight from the
+//                                    registers the unrolled steps produced them in;
+//   blkrec[seg * BLK_STRIDE + k]     the record offset of the DC record of the segment's k-th block;
+//   seg_nrec[seg]                    records written, seg_dc[seg] the sum of the segment's DC deltas (I frames).
+// After this pass no kernel touches the bitstream again: k_entropy_tiles turns the per-segment tables into one
+// descriptor per tile of 32 blocks, and the block-parallel decode kernels (decode.cu) read the records with
+// coalesced, look-ahead copies instead of a bit-serial dependent chain.
 // ------------------------------------------------------------------------------------------------
-// Small CTAs, one segment per lane: measured best (3.75 ms / 2000 frames at 1080p; pools of 2 / 4 / 8 segments per
-// lane pulled from the CTA-wide counter: 4.0 / 4.45 / 4.8 ms) -- the hardware CTA scheduler balances many short CTAs
-// better than lanes balance inside a long-lived one.  The pull loop below stays general (INDEX_SLOTS >= INDEX_TPB).
-constexpr int INDEX_TPB = 64;
-constexpr int INDEX_SLOTS = 64;      // segments per CTA
+constexpr int EMIT_TPB = 64;         // small CTAs, one segment per lane: the hardware CTA scheduler balances the load
+
+// Blocks of segment g that exist in its plane (trailing pad bits can look like blocks).
+__device__ __forceinline__ uint32_t seg_blocks(const uint32_t* __restrict__ seg_cnt, uint32_t g, uint32_t first, uint32_t nb) {
+    return first >= nb ? 0u : min(seg_cnt[g], nb - first);
+}
 
 template <bool FOLD>
-__global__ void __launch_bounds__(INDEX_TPB, 16)
-k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
-                const uint32_t* __restrict__ seg_stream, uint32_t seg_lo, uint32_t seg_hi,
-                const uint32_t* __restrict__ seg_entry, const uint32_t* __restrict__ seg_cnt,
-                const uint32_t* __restrict__ seg_first, uint32_t* __restrict__ seg_dc, uint2* __restrict__ blk_info,
-                uint32_t* __restrict__ sym, uint32_t sym_seg0, unsigned long long* __restrict__ n_entries) {
-    __shared__ uint32_t s_next;
-    const int t = threadIdx.x;
-    const uint32_t g0 = seg_lo + blockIdx.x * INDEX_SLOTS;
-    const uint32_t k_hi = min((uint32_t)INDEX_SLOTS, seg_hi - g0);
-    if (t == 0) s_next = INDEX_TPB;
-    __syncthreads();
-
+__global__ void __launch_bounds__(EMIT_TPB, 16)
+k_entropy_emit(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
+               const uint32_t* __restrict__ seg_stream, uint32_t seg_lo, uint32_t seg_hi,
+               const uint32_t* __restrict__ seg_entry, const uint32_t* __restrict__ seg_cnt,
+               const uint32_t* __restrict__ seg_first, uint32_t* __restrict__ rec, uint16_t* __restrict__ blkrec, uint32_t seg0,
+               unsigned long long* __restrict__ n_entries) {
+    const uint32_t g = seg_lo + blockIdx.x * EMIT_TPB + threadIdx.x;
     Parser ps;
     ps.init_parked();
-    uint32_t g = 0, cnt = 0, k = 0, o = 0, o_blk = 0, o_end = 0, written = 0, tag = 0;
-    uint2* bi = nullptr;
+    // The lane writes the record offset of the DC record of each of its cnt blocks AND of the block after them:
+    // blkrec[cnt] is the number of records the segment holds.  bo .. bend = table entries still to write.
+    uint32_t bo = 0, bend = 0, ro = 0;
     int cur = 0;
-    bool pframe = false;
-    uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // the last (o & 7) entries, newest in q[7]: stored one full 32-byte
-                                               // sector at a time (a partial-sector store makes L2 fetch the rest)
-    // Take segments from the CTA's counter until one holds blocks (cnt != 0) or none is left (cnt == 0).
-    auto grab = [&](uint32_t slot) {
-        for (;; slot = atomicAdd(&s_next, 1u)) {
-            k = 0; cnt = 0;
-            if (slot >= k_hi) { ps.park(); return; }
-            g = g0 + slot;
-            const SegCtx c = seg_ctx(payload, streams, seg_stream, g);
-            const StreamDesc* sd = streams + c.sid;
-            const uint32_t nb = sd->nb, first = seg_first[g];
-            cnt = first >= nb ? 0u : min(seg_cnt[g], nb - first);   // trailing pad bits can look like blocks
-            // A stream that ends early leaves the remaining blocks empty (zero coefficients).
-            if (c.seg + 1u == sd->nseg)
-                for (uint32_t b = first + cnt; b < nb; b++) blk_info[sd->block_base + b] = make_uint2(BLK_NO_SEG, 0);
-            if (cnt == 0) { seg_dc[g] = 0u; continue; }
+    bool iframe = false;
+    if (g < seg_hi) {
+        const SegCtx c = seg_ctx(payload, streams, seg_stream, g);
+        const StreamDesc* sd = streams + c.sid;
+        const uint32_t cnt = seg_blocks(seg_cnt, g, seg_first[g], sd->nb);
+        bo = bend = (g - seg0) * BLK_STRIDE;
+        if (cnt) {
             ps.start(c.base, seg_entry[g] + c.bias, c.seg_start + SEG_BITS, c.ftotal);
-            bi = blk_info + sd->block_base + first;
-            tag = (first & 31u) << 6;                    // (index of the block being parsed & 31) << 6
-            o = o_blk = (g - sym_seg0) * SYM_STRIDE;     // chunk-relative entry index
-            o_end = o + SYM_STRIDE;
-            cur = 0;
-            pframe = sd->ptype != 0;
-            return;
+            bend = bo + cnt + 1u;
+            ro = (g - seg0) * REC_STRIDE;
+            iframe = sd->ptype == 0;
+        } else {
+            blkrec[bo] = 0;
         }
-    };
-    grab((uint32_t)t);
-    // (four steps per look at the loop condition: a lane that is done is parked, extra steps change nothing)
-    auto one_step = [&]() {
-        Parser::Sym y;
-        const bool end = ps.step<true, FOLD>(y);
-        if (y.dc) { cur = pframe ? y.e : cur + y.e; o_blk = o; }
-        if (y.coded && y.at < (64u << 24)) {             // (a parked lane never sees a coded symbol)
-#pragma unroll
-            for (int i = 0; i < 7; i++) q[i] = q[i + 1];
-            q[7] = (y.at >> 24) | tag | ((uint32_t)y.e << 16);
-            o++;
-            if ((o & 7u) == 0u && o <= o_end) st_global_v8(sym + o - 8, q);   // never overflows on conforming streams
-        }
-        if (end && k < cnt) {
-            bi[k] = make_uint2(min(o_blk, o_end - 1u), ((uint32_t)cur & 0xFFFFu) | ((min(o, o_end) - min(o_blk, o_end)) << 16));
-            tag = (tag + 64u) & 0x7C0u;
-            if (++k == cnt) {                            // segment done
-                seg_dc[g] = pframe ? 0u : ((uint32_t)cur & 0xFFFFu);
-                if ((o & 7u) && o < o_end) {             // flush the partial group (entries beyond o are never read)
-                    const uint32_t r = o & 7u;
-                    uint32_t v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {        // v[i] = q[8 - r + i] for i < r
-                        uint32_t x = 0;
-#pragma unroll
-                        for (int j = 1; j < 8; j++) if ((uint32_t)j == r && 8 - j + i < 8) x = q[8 - j + i];
-                        v[i] = x;
-                    }
-                    st_global_v8(sym + (o & ~7u), v);
-                }
-                written += min(o, o_end) - (o_end - SYM_STRIDE);
-                grab(atomicAdd(&s_next, 1u));
-            }
-        }
-    };
-    while (__any_sync(FULL_MASK, cnt != 0u)) {
-        one_step();
-        one_step();
-        one_step();
-        one_step();
     }
-    {   // statistics: list entries written by this launch (one atomic per warp)
+    uint32_t o = 0;                      // records so far (warp-uniform)
+    const uint32_t bo0 = bo;
+    while (__any_sync(FULL_MASK, bo != bend)) {
+        uint32_t q[8];
+        const bool wr = bo != bend;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            Parser::Sym y;
+            ps.step<true, FOLD>(y);
+            if (y.dc) cur += y.e;        // I frames: the running sum `cur` of lossless_decode.c:94; P frames record the delta (:91)
+            const uint32_t lo = y.dc ? REC_DC : (y.coded ? (y.at >> 24) : REC_NONE);
+            q[j] = lo | ((uint32_t)((y.dc && iframe) ? cur : y.e) << 16);
+            if (y.dc && bo != bend) { asm volatile("st.global.L1::no_allocate.u16 [%0], %1;" ::"l"(blkrec + bo), "h"((uint16_t)(o + j)) : "memory"); bo++; }
+        }
+        if (wr) st_global_v8(rec + ro + o, q);
+        o += 8u;
+        if (bo == bend) ps.park();       // done (at most 8 steps past its last block: inside the payload's padding)
+        if (o == REC_STRIDE) {           // non-conforming input: the region is full, the rest of the segment is dropped
+            for (; bo != bend; bo++) blkrec[bo] = (uint16_t)o;
+            break;
+        }
+    }
+    {   // statistics: records written by this launch (one atomic per warp)
+        uint32_t written = bend != bo0 ? blkrec[bend - 1u] : 0u;
 #pragma unroll
         for (int d = 16; d; d >>= 1) written += __shfl_xor_sync(FULL_MASK, written, d);
-        if ((t & 31) == 0 && written) atomicAdd(n_entries, (unsigned long long)written);
+        if ((threadIdx.x & 31) == 0 && written) atomicAdd(n_entries, (unsigned long long)written);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// DC predictors: one warp per stream turns seg_dc (the segments' DC totals) into the exclusive prefix
-// sum mod 2^16 = the value of `cur` (lossless_decode.c:73,94) entering each segment.
+// Tile descriptors: one thread per segment writes the descriptor of every tile (32 consecutive blocks of the plane)
+// whose FIRST block the segment owns -- every existing block has exactly one owner, so every tile has one writer;
+// the tiles past a stream's last block (a stream that ends early leaves the remaining blocks empty = zero
+// coefficients) are written by the thread of the stream's last segment.  Runs after k_entropy_dcscan: fast.w
+// carries the DC predictors entering the first two runs' segments.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-k_entropy_dcscan(const StreamDesc* __restrict__ streams, uint32_t n_streams, uint32_t* __restrict__ seg_dc) {
+k_entropy_tiles(const StreamDesc* __restrict__ streams, const uint32_t* __restrict__ seg_stream, uint32_t seg_lo,
+                uint32_t seg_hi, const uint32_t* __restrict__ seg_cnt, const uint32_t* __restrict__ seg_first,
+                const uint32_t* __restrict__ seg_dc, const uint32_t* __restrict__ seg_nrec,
+                const uint16_t* __restrict__ blkrec, uint32_t seg0, TileDesc* __restrict__ tiles, uint32_t stream0) {
+    const uint32_t g = seg_lo + blockIdx.x * 128u + threadIdx.x;
+    if (g >= seg_hi) return;
+    const uint32_t sid = __ldg(seg_stream + g);
+    const StreamDesc sd = streams[sid];
+    if (g - sd.seg_base >= sd.nseg) return;                           // a padding segment (SUPER alignment)
+    const uint32_t nb = sd.nb, tpp = (nb + 31u) / 32u;
+    TileDesc* td = tiles + (size_t)(sid - stream0) * tpp;
+    const uint32_t g_end = sd.seg_base + sd.nseg;                      // the stream's segments are [seg_base, g_end)
+    auto blocks_of = [&](uint32_t s, uint32_t& first) {
+        first = seg_first[s];
+        return seg_blocks(seg_cnt, s, first, nb);
+    };
+    uint32_t first;
+    const uint32_t cnt = blocks_of(g, first);
+    const uint32_t stop = min(first, nb) + cnt;                        // blocks [first, stop) are this segment's
+    for (uint32_t T = (first + 31u) / 32u; T * 32u < stop; T++) {
+        const uint32_t b0 = T * 32u, b1 = min(b0 + 32u, nb);
+        const uint16_t* br = blkrec + (size_t)(g - seg0) * BLK_STRIDE;
+        const uint32_t r0 = br[b0 - first];
+        TileDesc d;
+        d.fast.x = (g - seg0) * REC_STRIDE + r0;
+        d.fast.w = seg_dc[g];
+        d.fast.y = 0u;
+        d.slow = make_uint4(g + 1u, 1u, 0u, 0u);
+        if (b1 <= stop) {                                              // the tile ends inside this segment
+            d.fast.z = (b1 < stop ? (uint32_t)br[b1 - first] : seg_nrec[g]) - r0;
+        } else {
+            uint32_t n0 = seg_nrec[g] - r0, n1 = 0u, nruns = 1u, nlast = 0u;
+            for (uint32_t s = g + 1u; s < g_end; s++) {               // the following segments of the stream
+                uint32_t f2;
+                const uint32_t c2 = blocks_of(s, f2);
+                nruns++;
+                const bool last = f2 + c2 >= b1 || s + 1u == g_end;
+                const uint32_t n = (c2 && b1 < f2 + c2) ? (uint32_t)blkrec[(size_t)(s - seg0) * BLK_STRIDE + (b1 - f2)]
+                                                         : (c2 ? seg_nrec[s] : 0u);
+                if (s == g + 1u) { n1 = n; d.fast.w |= seg_dc[s] << 16; d.fast.y = (s - seg0) * REC_STRIDE; }
+                if (last) { nlast = n; break; }
+            }
+            d.fast.z = n0 | (n1 << 16);
+            if (nruns > 2u) d.fast.y |= TILE_MORE;
+            d.slow.y = nruns; d.slow.z = nlast;
+        }
+        td[T] = d;
+    }
+    if (g + 1u == g_end) {                                             // tiles without any block
+        TileDesc z;
+        z.fast = make_uint4(0u, 0u, 0u, 0u); z.slow = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t T = (stop + 31u) / 32u; T < tpp; T++) td[T] = z;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DC predictors: one warp per stream.  A segment's DC total is the running sum in the DC record of its last block
+// (I frames; P-frame DC symbols are deltas against the previous frame: no predictor); the exclusive prefix sum mod
+// 2^16 of the totals is the value of `cur` (lossless_decode.c:73,94) entering each segment -> seg_dc.  Also copies the
+// segment's record count, blkrec[cnt], to seg_nrec.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_entropy_dcscan(const StreamDesc* __restrict__ streams, uint32_t n_streams, const uint32_t* __restrict__ seg_cnt,
+                 const uint32_t* __restrict__ seg_first, const uint32_t* __restrict__ rec, const uint16_t* __restrict__ blkrec,
+                 uint32_t seg0, uint32_t* __restrict__ seg_dc, uint32_t* __restrict__ seg_nrec) {
     const uint32_t s = blockIdx.x * 4u + (threadIdx.x >> 5);
     if (s >= n_streams) return;
     const StreamDesc sd = streams[s];
     const int lane = threadIdx.x & 31;
-    uint32_t* v = seg_dc + sd.seg_base;
     uint32_t carry = 0;
     for (uint32_t i0 = 0; i0 < sd.nseg; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const uint32_t x = i < sd.nseg ? v[i] : 0u;
+        const uint32_t i = i0 + lane, g = sd.seg_base + i;
+        uint32_t x = 0;
+        if (i < sd.nseg) {
+            const uint32_t cnt = seg_blocks(seg_cnt, g, seg_first[g], sd.nb);
+            const uint16_t* br = blkrec + (size_t)(g - seg0) * BLK_STRIDE;
+            seg_nrec[g] = br[cnt];
+            if (cnt && sd.ptype == 0) x = rec[(size_t)(g - seg0) * REC_STRIDE + br[cnt - 1u]] >> 16;
+        }
         uint32_t inc = x;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t a = __shfl_up_sync(FULL_MASK, inc, d);
             if (lane >= d) inc += a;
         }
-        if (i < sd.nseg) v[i] = (carry + inc - x) & 0xFFFFu;
+        if (i < sd.nseg) seg_dc[g] = (carry + inc - x) & 0xFFFFu;
         carry += __shfl_sync(FULL_MASK, inc, 31);
     }
 }
@@ -571,21 +606,23 @@ cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s) {
                                                       j.d_stream_blocks + j.stream_lo, j.d_fixups);
     return cudaGetLastError();
 }
-cudaError_t launch_entropy_index(const EntropyJob& j, cudaStream_t s) {
+cudaError_t launch_entropy_emit(const EntropyJob& j, cudaStream_t s) {
     if (j.seg_hi <= j.seg_lo) return cudaSuccess;
     const uint32_t n = j.seg_hi - j.seg_lo;
-    const unsigned grid = (n + INDEX_SLOTS - 1) / INDEX_SLOTS;
+    const unsigned grid = (n + EMIT_TPB - 1) / EMIT_TPB;
     if (j.fold_end)
-        k_entropy_index<true><<<grid, INDEX_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry,
-                                                         j.d_seg_cnt, j.d_seg_first, j.d_seg_dc, j.d_blk_info, j.d_sym, j.sym_seg0,
-                                                         j.d_fixups + 1);
+        k_entropy_emit<true><<<grid, EMIT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry,
+                                                       j.d_seg_cnt, j.d_seg_first, j.d_rec, j.d_blkrec, j.seg0, j.d_fixups + 1);
     else
-        k_entropy_index<false><<<grid, INDEX_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry,
-                                                          j.d_seg_cnt, j.d_seg_first, j.d_seg_dc, j.d_blk_info, j.d_sym, j.sym_seg0,
-                                                          j.d_fixups + 1);
+        k_entropy_emit<false><<<grid, EMIT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry,
+                                                        j.d_seg_cnt, j.d_seg_first, j.d_rec, j.d_blkrec, j.seg0, j.d_fixups + 1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k_entropy_dcscan<<<(j.n_streams + 3) / 4, 128, 0, s>>>(j.d_streams + j.stream_lo, j.n_streams, j.d_seg_dc);
+    k_entropy_dcscan<<<(j.n_streams + 3) / 4, 128, 0, s>>>(j.d_streams + j.stream_lo, j.n_streams, j.d_seg_cnt, j.d_seg_first, j.d_rec,
+                                                          j.d_blkrec, j.seg0, j.d_seg_dc, j.d_seg_nrec);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    k_entropy_tiles<<<(n + 127) / 128, 128, 0, s>>>(j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_cnt, j.d_seg_first,
+                                                    j.d_seg_dc, j.d_seg_nrec, j.d_blkrec, j.seg0, j.d_tiles, j.stream_lo);
     return cudaGetLastError();
 }
 

@@ -40,11 +40,17 @@ int parse_mpg(const uint8_t* mpg, size_t len, MpgIndex& idx, bool headers_only) 
         set_error("mpg: width and height must be non-zero multiples of 8");   // mjpeg423_decoder.c:45-48: no edge handling
         return MJPEG423_E_ARG;
     }
+    // (W/8)*(H/8) must stay well inside 32 bits: block indices and bit positions are 32-bit throughout
+    if ((uint64_t)(in.w_size / 8) * (in.h_size / 8) > MAX_PLANE_BLOCKS) {
+        set_error("mpg: picture too large (more than 2^24 blocks per plane)");
+        return MJPEG423_E_ARG;
+    }
     in.frame_bytes = (uint64_t)in.w_size * in.h_size * 4;
     in.num_pframes = 0; in.max_frame_payload = 0;
     idx.frames.clear();
     if (headers_only && in.num_frames == 0) return MJPEG423_OK;
-    idx.frames.reserve(in.num_frames);
+    // num_frames is untrusted: a frame takes at least its 16-byte header, so the file length bounds the reserve
+    idx.frames.reserve((size_t)std::min<uint64_t>(in.num_frames, (len - 20) / 16));
     uint64_t off = 20;
     for (uint32_t f = 0; f < in.num_frames; f++) {
         if (off + 16 > len) { set_error("mpg: truncated at frame header " + std::to_string(f)); return MJPEG423_E_FORMAT; }
@@ -143,6 +149,21 @@ void make_chunks(const Plan& plan, uint32_t K, std::vector<Chunk>& chunks, std::
     }
 }
 
+size_t chunk_scratch_bytes(size_t segs, size_t streams, uint32_t nb) {
+    const size_t tpp = (nb + 31u) / 32u;
+    return ((streams * tpp * sizeof(TileDesc) + 255) & ~(size_t)255) + segs * (size_t)REC_STRIDE * 4 +
+           ((segs * (size_t)BLK_STRIDE * 2 + 255) & ~(size_t)255) + 256;
+}
+void carve_chunk_scratch(EntropyJob& j, void* base, size_t segs, size_t streams, uint32_t nb) {
+    const size_t tpp = (nb + 31u) / 32u;
+    uint8_t* w = static_cast<uint8_t*>(base);
+    j.d_tiles = reinterpret_cast<TileDesc*>(w);
+    w += (streams * tpp * sizeof(TileDesc) + 255) & ~(size_t)255;
+    j.d_rec = reinterpret_cast<uint32_t*>(w);
+    w += segs * (size_t)REC_STRIDE * 4;
+    j.d_blkrec = reinterpret_cast<uint16_t*>(w);
+}
+
 }  // namespace mj
 
 using namespace mj;
@@ -215,7 +236,7 @@ extern "C" void mjpeg423_b200_destroy(mjpeg423_b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&c->payload, &c->tables, &c->segs, &c->coef[0], &c->coef[1], &c->blkidx[0], &c->blkidx[1],
-                      &c->samples, &c->stream_blocks, &c->misc, &c->ids, &c->in_ring[0], &c->in_ring[1], &c->out_ring[0],
+                      &c->samples[0], &c->samples[1], &c->stream_blocks, &c->misc, &c->ids, &c->in_ring[0], &c->in_ring[1], &c->out_ring[0],
                       &c->out_ring[1], &c->fstate[0], &c->fstate[1]})
         b->release();
     for (int i = 0; i < 2; i++) if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
@@ -263,7 +284,7 @@ namespace {
 
 struct Tables {           // device addresses inside ctx->tables / ctx->segs
     StreamDesc* streams;
-    uint32_t *seg_stream, *seg_entry, *seg_exit, *seg_cnt, *seg_first, *seg_dc, *stream_blocks;
+    uint32_t *seg_stream, *seg_entry, *seg_exit, *seg_cnt, *seg_first, *seg_dc, *seg_nrec, *stream_blocks;
     unsigned long long* fixups;
 };
 
@@ -281,8 +302,9 @@ Tables tables_of(mjpeg423_b200_ctx* c, const Plan& plan) {
     t.seg_first = reinterpret_cast<uint32_t*>(sb + 3 * b_seg);
     t.seg_dc = reinterpret_cast<uint32_t*>(sb + 4 * b_seg);
     t.seg_stream = reinterpret_cast<uint32_t*>(sb + 5 * b_seg);
-    t.stream_blocks = reinterpret_cast<uint32_t*>(sb + 6 * b_seg);
-    t.fixups = reinterpret_cast<unsigned long long*>(sb + 6 * b_seg + b_sb);
+    t.seg_nrec = reinterpret_cast<uint32_t*>(sb + 6 * b_seg);
+    t.stream_blocks = reinterpret_cast<uint32_t*>(sb + 7 * b_seg);
+    t.fixups = reinterpret_cast<unsigned long long*>(sb + 7 * b_seg + b_sb);
     return t;
 }
 
@@ -291,7 +313,7 @@ int upload_tables(mjpeg423_b200_ctx* c, const Plan& plan, Tables& t, cudaStream_
     int rc = c->tables.reserve(plan.streams.size() * sizeof(StreamDesc) + 256);
     if (rc) return rc;
     const size_t nseg = plan.f_seg0.empty() ? 0 : plan.f_seg0.back();
-    rc = c->segs.reserve(6 * align256(nseg * 4) + align256(plan.streams.size() * 4) + 256);   // ... + 2 x u64 counters
+    rc = c->segs.reserve(7 * align256(nseg * 4) + align256(plan.streams.size() * 4) + 256);   // ... + 2 x u64 counters
     if (rc) return rc;
     t = tables_of(c, plan);
     CU(cudaMemcpyAsync(t.streams, plan.streams.data(), plan.streams.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, s));
@@ -332,11 +354,10 @@ int decode_mode(const mjpeg423_b200_ctx* c, const Plan& plan) {
     return c->staged;
 }
 
-// Per-chunk scratch: block index (8 bytes per block) + symbol lists (SYM_STRIDE entries per segment) and,
-// in the staged modes, coefficient planes.
+// Per-chunk scratch: tile descriptors + record lists (REC_STRIDE records per segment) + block tables (BLK_STRIDE
+// u16 per segment) and, in the staged modes, coefficient planes.
 size_t chunk_index_bytes(const Plan& plan, uint32_t f0, uint32_t f1) {
-    const size_t blocks = (size_t)(f1 - f0) * 3 * plan.nb, segs = plan.f_seg0[f1] - plan.f_seg0[f0];
-    return blocks * 8 + 32 + segs * (size_t)SYM_STRIDE * 4 + 256;
+    return chunk_scratch_bytes(plan.f_seg0[f1] - plan.f_seg0[f0], (size_t)(f1 - f0) * 3, plan.nb);
 }
 int reserve_chunk_buffers(mjpeg423_b200_ctx* c, const Plan& plan, const std::vector<Chunk>& chunks, int nbuf) {
     size_t idx_bytes = 0, frames = 0;
@@ -349,8 +370,9 @@ int reserve_chunk_buffers(mjpeg423_b200_ctx* c, const Plan& plan, const std::vec
         int rc = c->blkidx[i].reserve(idx_bytes);
         if (rc) return rc;
         if (decode_mode(c, plan) && (rc = c->coef[i].reserve(blocks * 128))) return rc;
+        // (every buffer in flight owns its sample planes too: two chunks run concurrently on s_compute / s_aux)
+        if (decode_mode(c, plan) == 2 && (rc = c->samples[i].reserve(blocks * 64))) return rc;
     }
-    if (decode_mode(c, plan) == 2) return c->samples.reserve(blocks * 64);
     return MJPEG423_OK;
 }
 
@@ -370,13 +392,9 @@ EntropyJob make_job(const Plan& plan, const Tables& t, const uint8_t* d_payload_
     j.d_seg_entry = t.seg_entry; j.d_seg_exit = t.seg_exit; j.d_seg_cnt = t.seg_cnt; j.d_seg_first = t.seg_first;
     j.d_seg_dc = t.seg_dc;
     j.d_stream_blocks = t.stream_blocks; j.d_fixups = t.fixups;
-    // StreamDesc.block_base is plan-relative: shift the chunk buffers back by the chunk's first block
-    // ... and StreamDesc.seg_base too: same for the symbol lists
-    const size_t blocks = (size_t)(f1 - f0) * 3 * plan.nb, first_block = (size_t)f0 * 3 * plan.nb;
-    uint32_t* w = static_cast<uint32_t*>(d_blkidx);
-    j.d_blk_info = reinterpret_cast<uint2*>(w) - first_block;
-    j.d_sym = w + ((2 * blocks + 7) & ~(size_t)7);   // 32-byte aligned; entries are relative to the chunk's first segment
-    j.sym_seg0 = plan.f_seg0[f0];
+    j.d_seg_nrec = t.seg_nrec;
+    j.seg0 = plan.f_seg0[f0];
+    carve_chunk_scratch(j, d_blkidx, j.seg_hi - j.seg_lo, j.n_streams, plan.nb);
     return j;
 }
 
@@ -396,9 +414,9 @@ int enqueue_chunk(mjpeg423_b200_ctx* c, const Plan& plan, const Tables& t, const
     if (prof) CU(cudaEventRecord(prof[1], s));
     if (!synced) CU(launch_entropy_chain(j, s));
     if (prof) CU(cudaEventRecord(prof[2], s));
-    CU(launch_entropy_index(j, s));
+    CU(launch_entropy_emit(j, s));
     if (prof) CU(cudaEventRecord(prof[3], s));
-    c->stats.kernel_launches += synced ? 2 : 4;
+    c->stats.kernel_launches += synced ? 3 : 5;       // emit + DC scan + tile descriptors (+ sync + chain)
     if (mode == 0) {
         const uint32_t* d_gops = nullptr;
         if (plan.n_pframes) {                    // GOP-walking variant; its scratch belongs to this chunk buffer
@@ -421,9 +439,9 @@ int enqueue_chunk(mjpeg423_b200_ctx* c, const Plan& plan, const Tables& t, const
     }
     if (prof) CU(cudaEventRecord(prof[4], s));
     if (mode == 2) {
-        CU(launch_idct(d_coef, c->samples.as<uint8_t>(), (size_t)(f1 - f0) * 3 * plan.nb, s));
+        CU(launch_idct(d_coef, c->samples[buf].as<uint8_t>(), (size_t)(f1 - f0) * 3 * plan.nb, s));
         if (prof) CU(cudaEventRecord(prof[5], s));
-        CU(launch_colour(c->samples.as<uint8_t>(), d_out, f1 - f0, plan.W, plan.H, s));
+        CU(launch_colour(c->samples[buf].as<uint8_t>(), d_out, f1 - f0, plan.W, plan.H, s));
         if (prof) { CU(cudaEventRecord(prof[6], s)); CU(cudaEventRecord(prof[7], s)); }
         c->stats.kernel_launches += 2;
     } else {
@@ -485,13 +503,13 @@ extern "C" int mjpeg423_b200_upload(mjpeg423_b200_ctx* c, const uint8_t* mpg, si
     rc = build_plan(idx, first, n, c->plan);
     if (rc) return rc;
     if (n == 0) { c->have_plan = true; return MJPEG423_OK; }
-    rc = c->payload.reserve(c->plan.payload_len + 64);       // + look-ahead pad
+    rc = c->payload.reserve(c->plan.payload_len + PAYLOAD_PAD);       // + look-ahead pad
     if (rc) return rc;
     Tables t;
     rc = upload_tables(c, c->plan, t, c->s_compute);
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->payload.p, mpg + c->plan.payload_off, c->plan.payload_len, cudaMemcpyHostToDevice, c->s_compute));
-    CU(cudaMemsetAsync(c->payload.as<uint8_t>() + c->plan.payload_len, 0, 64, c->s_compute));
+    CU(cudaMemsetAsync(c->payload.as<uint8_t>() + c->plan.payload_len, 0, PAYLOAD_PAD, c->s_compute));
     CU(cudaStreamSynchronize(c->s_compute));
     c->have_plan = true;
     return MJPEG423_OK;
@@ -505,10 +523,11 @@ extern "C" int mjpeg423_b200_decode_resident(mjpeg423_b200_ctx* c, void* d_out) 
     if (plan.n == 0) return MJPEG423_OK;
     if (!d_out) return MJPEG423_E_ARG;
     Tables t = tables_of(c, plan);
-    // chunk size: bounded scratch (block index 6 B/block, + 128 B/block of coefficients in the staged modes)
-    const size_t scratch_frame = (size_t)3 * plan.nb * (decode_mode(c, plan) ? 136 : 8) +
-                                 (size_t)(plan.f_seg0.back() / plan.n + 1) * SYM_STRIDE * 4;
-    const uint32_t K = c->chunk_frames ? std::min(c->chunk_frames, plan.n) : auto_chunk(plan, (uint64_t)3 << 30, scratch_frame);
+    // chunk size: bounded scratch (records + block tables + tile descriptors, + 128 B/block of coefficients and 64 of
+    // samples in the staged modes)
+    const size_t scratch_frame = chunk_scratch_bytes(plan.f_seg0.back() / plan.n + 1, 3, plan.nb) +
+                                 (size_t)3 * plan.nb * (decode_mode(c, plan) == 2 ? 192 : decode_mode(c, plan) ? 128 : 0);
+    const uint32_t K = c->chunk_frames ? std::min(c->chunk_frames, plan.n) : auto_chunk(plan, (uint64_t)4 << 30, scratch_frame);
     int rc = prepare_chunks(c, plan, K, c->s_compute);
     if (rc) return rc;
     const int nbuf = (c->chunks.size() > 1 && !c->profile) ? 2 : 1;
@@ -588,7 +607,7 @@ extern "C" int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* c, int16_t* d_c
     CU(cudaEventRecord(e[1], s));
     CU(launch_entropy_chain(j, s));
     CU(cudaEventRecord(e[2], s));
-    CU(launch_entropy_index(j, s));
+    CU(launch_entropy_emit(j, s));
     CU(cudaEventRecord(e[3], s));
     const uint32_t* ids = c->ids.as<uint32_t>() + ch.ids_off;
     for (size_t l = 0; l + 1 < ch.level_off.size(); l++) {
@@ -596,7 +615,7 @@ extern "C" int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* c, int16_t* d_c
         c->stats.kernel_launches += 1;
     }
     CU(cudaEventRecord(e[4], s));
-    c->stats.kernel_launches += 4;
+    c->stats.kernel_launches += 5;
     rc = finish_stats(c, plan, t, s);
     CU(cudaEventElapsedTime(&c->stats.total_ms, e[0], e[4]));
     CU(cudaEventElapsedTime(&c->stats.sync_ms, e[0], e[1]));
@@ -668,7 +687,7 @@ extern "C" int mjpeg423_b200_decode_frames(mjpeg423_b200_ctx* c, const uint8_t* 
     for (const Chunk& ch : c->chunks)
         max_in = std::max<size_t>(max_in, plan.frames[ch.f1 - 1].off + plan.frames[ch.f1 - 1].size - plan.frames[ch.f0].off);
     for (int i = 0; i < 2; i++) {
-        if ((rc = c->in_ring[i].reserve(max_in + 64))) return rc;
+        if ((rc = c->in_ring[i].reserve(max_in + PAYLOAD_PAD))) return rc;
         if (!out_on_device && (rc = c->out_ring[i].reserve((size_t)maxf * frame_bytes))) return rc;
     }
     cudaEvent_t ev_start = c->ev[0], ev_stop = c->ev[1];
@@ -688,7 +707,7 @@ extern "C" int mjpeg423_b200_decode_frames(mjpeg423_b200_ctx* c, const uint8_t* 
         // upload: the slot is free once the chunk that used it two iterations ago has been decoded
         if (k >= 2) CU(cudaStreamWaitEvent(c->s_in, ev_comp[b], 0));
         CU(cudaMemcpyAsync(c->in_ring[b].p, mpg + in_off, in_len, cudaMemcpyHostToDevice, c->s_in));
-        CU(cudaMemsetAsync(c->in_ring[b].as<uint8_t>() + in_len, 0, 64, c->s_in));
+        CU(cudaMemsetAsync(c->in_ring[b].as<uint8_t>() + in_len, 0, PAYLOAD_PAD, c->s_in));
         CU(cudaEventRecord(ev_in[b], c->s_in));
         // decode
         CU(cudaStreamWaitEvent(c->s_compute, ev_in[b], 0));
