@@ -61,8 +61,8 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     if ((rc = s_in.reserve(len + PAYLOAD_PAD))) return rc;
     if ((rc = s_tab.reserve(256 + 256))) return rc;
     const uint32_t nseg_pad = (sd.nseg + SUPER - 1) / SUPER * SUPER;      // global segment numbering is SUPER-aligned
-    if ((rc = s_seg.reserve((size_t)nseg_pad * 32 + 96))) return rc;
-    if ((rc = s_idx.reserve(chunk_scratch_bytes(nseg_pad, 1, sd.nb)))) return rc;
+    if ((rc = s_seg.reserve((size_t)nseg_pad * 28 + 96))) return rc;
+    if ((rc = s_idx.reserve(chunk_scratch_bytes(nseg_pad, (size_t)num_blocks)))) return rc;
     if ((rc = s_mid.reserve(coef_bytes))) return rc;
     uint8_t* tab = s_tab.as<uint8_t>();
     int16_t* d_q = reinterpret_cast<int16_t*>(tab);                  // 128 int16 (table 0 used)
@@ -84,11 +84,10 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     j.d_seg_entry = seg; j.d_seg_exit = seg + nseg_pad; j.d_seg_cnt = seg + 2 * (size_t)nseg_pad;
     j.d_seg_first = seg + 3 * (size_t)nseg_pad;
     j.d_seg_dc = seg + 4 * (size_t)nseg_pad;
-    j.d_seg_nrec = seg + 6 * (size_t)nseg_pad;
-    j.d_stream_blocks = seg + 7 * (size_t)nseg_pad;
-    j.d_fixups = reinterpret_cast<unsigned long long*>(seg + ((7 * (size_t)nseg_pad + 3) & ~(size_t)1));
+    j.d_stream_blocks = seg + 6 * (size_t)nseg_pad;
+    j.d_fixups = reinterpret_cast<unsigned long long*>(seg + ((6 * (size_t)nseg_pad + 3) & ~(size_t)1));
     j.seg0 = 0;
-    carve_chunk_scratch(j, s_idx.p, nseg_pad, 1, sd.nb);
+    carve_chunk_scratch(j, s_idx.p, (size_t)num_blocks, 0);
     uint32_t* d_ids = reinterpret_cast<uint32_t*>(tab + 256 + 128);     // one id: stream 0
     CUX(cudaMemsetAsync(d_ids, 0, 4, s));
     CUX(cudaMemsetAsync(j.d_fixups, 0, 16, s));

@@ -26,32 +26,23 @@ constexpr uint32_t MAX_STREAM_BYTES = 1u << 28; // bit positions are 32-bit
 constexpr uint32_t MAX_PLANE_BLOCKS = 1u << 24; // blocks per plane (W/8 * H/8): 32768 x 32768 pixels
 // Record lists: the emit pass (k_entropy_emit) writes ONE 32-bit record per symbol step of a segment's blocks into a
 // fixed-stride region (the steps of the lanes of a warp are synchronous, so the record position is the step count:
-// no compaction, no per-lane queue):
-//     bits 0..7  zig-zag index of a coded AC coefficient (1..63); 0 in a DC record; 255 = the step carried no
-//                coefficient (ZRL, a stand-alone END); other values >= 64 = non-conforming input, ignored
-//     bit 8      set for a block's DC symbol
-//     bits 16..31  AC: amplitude (HUFF_EXTEND, LIB/decoder/lossless_decode.c:204)
-//                  DC: I frames: the int16 running sum `cur` (:73,94) restarted at 0 at the segment's first block;
-//                      P frames: the DC delta itself (:91)
-// Every block starts with its DC record, so the consumers find block boundaries by counting bit 8.
+// no compaction, no per-lane queue, eight records leave as one 32-byte store):
+//     bits 0..7    zig-zag index of a coded AC coefficient (1..63); 0 in a DC record; 255 = the step carried no
+//                  coefficient (ZRL, a stand-alone END); other values >= 64 = non-conforming input, ignored
+//     bit 8        set for a block's DC symbol
+//     bits 9..13   (index of the block in its plane) & 31: the lane that owns the block in the decode kernels' warp
+//                  tiles of 32 consecutive blocks
+//     bits 16..31  AC: amplitude (HUFF_EXTEND, LIB/decoder/lossless_decode.c:204); DC: see BlockInfo
 // A conforming segment takes at most SEG_BITS / 6 steps that start inside it (DC size 0 + stand-alone END = two
 // steps per 12 bits) plus the rest of its last block (<= 68 steps): 751.
 constexpr uint32_t REC_STRIDE = 768;            // records per segment region, a multiple of 8 (32-byte sector stores)
 constexpr uint32_t REC_DC = 0x100u, REC_NONE = 0xFFu;
-// The record carries a coefficient: a DC record, or a coded AC coefficient with a conforming index.
-__device__ __forceinline__ bool rec_valid(uint32_t e) { return (e & 0xFFu) < 64u; }
-// blkrec: per segment, the record offset (u16) of every block's DC record, then the segment's record count;
-// <= SEG_BITS / MIN_BLOCK_BITS + 1 blocks.
-constexpr uint32_t BLK_STRIDE = 352;
-// Tile descriptor (k_entropy_tiles): where the records of 32 consecutive blocks of one plane lie.  They form one
-// run per bitstream segment the tile touches ("run" = a contiguous range of one segment's region).
-//   fast.x = record index of the tile's first record (the DC record of block 32 T), fast.y = first record of the
-//   second run | TILE_MORE when the tile has more than two runs, fast.z = records of the first run | of the second
-//   << 16, fast.w = DC predictor entering the first run's segment | the second's << 16 (I frames; 0 for P frames);
-//   slow.x = global segment of the second run, slow.y = number of runs, slow.z = records of the LAST run that belong
-//   to the tile (the runs between the second and the last are whole segments).
-struct TileDesc { uint4 fast, slow; };
-constexpr uint32_t TILE_MORE = 0x80000000u;
+// The record carries a coded AC coefficient with a conforming index.
+__device__ __forceinline__ bool rec_is_ac(uint32_t e) { return ((e & 0xFFu) - 1u) < 63u; }
+// Block index entry (uint2): .x = position of the block's first record (its DC record) -- always inside its segment's
+// region, so .x / REC_STRIDE names the segment (whose DC predictor the decode kernels add) -- or BLK_NO_SEG for a block
+// the stream does not hold; .y = segment-relative DC level | records of the block << 16.
+constexpr uint32_t BLK_NO_SEG = 0xFFFFFFFFu;
 
 // One plane bitstream of one frame (built by the host from the 16-byte frame headers,
 // LIB/decoder/mjpeg423_decoder.c:94-107).
@@ -121,7 +112,7 @@ struct FeedReg {
 // be aligned to its size (the slot address wraps with one LOP3).  Reads run up to 19 words past the window: the
 // payload buffer is padded by PAYLOAD_PAD bytes.
 constexpr int RING_WORDS = 32;
-constexpr size_t PAYLOAD_PAD = 128;
+constexpr size_t PAYLOAD_PAD = 320;
 template <int T>
 struct FeedRing {
     static constexpr uint32_t STRIDE = T * 4u, BYTES = RING_WORDS * STRIDE;
@@ -149,6 +140,26 @@ struct FeedRing {
     static __device__ __forceinline__ void wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 };
 
+// FeedSmem: the pass has copied the bytes the lane can reach into shared memory up front (k_entropy_emit: a segment
+// plus the longest block that can hang over its end); the window words are plain LDS, whose latency is short enough
+// for the per-step wait to be hidden by one or two other warps.
+struct FeedSmem {
+    uint32_t wa;           // shared address of the next word to take
+    uint32_t w2;           // look-ahead word (raw)
+    __device__ __forceinline__ uint32_t lds(uint32_t a) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void init_parked() { wa = 0u; w2 = 0u; }
+    __device__ __forceinline__ uint32_t take() {
+        const uint32_t r = __byte_perm(w2, 0, 0x0123);
+        w2 = lds(wa);
+        wa += 4u;
+        return r;
+    }
+};
+
 template <class Feed>
 struct ParserT {
     Feed fd;
@@ -170,6 +181,22 @@ struct ParserT {
         fd.start(w, feed_args...);
         fpos = fbits;
         flim = min(job_end + RUNAWAY_BITS, ftotal);
+        idx = 1u << 24;
+        nh = (uint32_t)-4;
+        rmask = 32u;
+    }
+    // FeedSmem only: the stream bytes from the aligned global address g0 on sit at shared address s0; a block is ended
+    // `guard` bits behind the job at the latest (the staged bytes end there).
+    __device__ __forceinline__ void start_smem(const uint8_t* base, uint32_t fbits, uint32_t job_end, uint32_t ftotal,
+                                               const uint8_t* g0, uint32_t s0, uint32_t guard) {
+        const uintptr_t w = (reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)3) + (size_t)(fbits >> 5) * 4u;
+        const uint32_t sw = s0 + (uint32_t)(w - reinterpret_cast<uintptr_t>(g0));
+        w0 = __byte_perm(fd.lds(sw), 0, 0x0123);
+        w1 = __byte_perm(fd.lds(sw + 4u), 0, 0x0123);
+        fd.w2 = fd.lds(sw + 8u);
+        fd.wa = sw + 12u;
+        fpos = fbits;
+        flim = min(job_end + guard, ftotal);
         idx = 1u << 24;
         nh = (uint32_t)-4;
         rmask = 32u;

@@ -25,6 +25,8 @@
 // Every pass advances with Parser::step() (common.cuh) in a UNIFORM loop: one step per iteration for
 // every lane, DC/AC and block-end handling predicated, the rare events (checkpoint, end of a job) in a
 // short divergent branch; a lane without work is parked.  Load balance comes from many small CTAs.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "runtime.h"
 
@@ -394,18 +396,32 @@ k_entropy_chain(const uint8_t* __restrict__ payload, const StreamDesc* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// Record lists.  Walking its blocks from the exact state, a segment's lane writes
+// Record lists + block index.  Walking its blocks from the exact state, a segment's lane writes
 //   rec[seg * REC_STRIDE + step]     one record per symbol step (layout: common.cuh); the lanes of a warp step in
 //                                    lock-step from step 0, so the record position is warp-uniform and eight
 //                                    consecutive records leave as ONE 32-byte sector store, straight from the
 //                                    registers the unrolled steps produced them in;
-//   blkrec[seg * BLK_STRIDE + k]     the record offset of the DC record of the segment's k-th block;
-//   seg_nrec[seg]                    records written, seg_dc[seg] the sum of the segment's DC deltas (I frames).
-// After this pass no kernel touches the bitstream again: k_entropy_tiles turns the per-segment tables into one
-// descriptor per tile of 32 blocks, and the block-parallel decode kernels (decode.cu) read the records with
-// coalesced, look-ahead copies instead of a bit-serial dependent chain.
+//   blk_info[block].x                index of the block's first record (its DC record; always inside the segment's
+//                                    region, so x / REC_STRIDE identifies the segment), or BLK_NO_SEG for a block the
+//                                    stream does not hold
+//   blk_info[block].y                DC level relative to the segment's entry (I frames: the int16 running sum `cur`
+//                                    of LIB/decoder/lossless_decode.c:73,94 restarted at 0; P frames: the DC delta
+//                                    itself, :91) | records of the block << 16
+// After this pass no kernel touches the bitstream again: the block-parallel decode kernels (decode.cu) read the
+// records with independent, look-ahead loads instead of a bit-serial dependent chain.
 // ------------------------------------------------------------------------------------------------
-constexpr int EMIT_TPB = 64;         // small CTAs, one segment per lane: the hardware CTA scheduler balances the load
+// One warp per CTA, one segment per lane.  Every lane first copies the bytes its parse can reach into its own
+// shared-memory region (16-byte cp.async): the segment, the longest block the reference decoder accepts hanging over its
+// end (19 + 63 x 23 = 1468 bits; EMIT_GUARD bits are allowed), the <= 7 steps a lane runs on after its last block, and
+// the window look-ahead.  The window words are then LDS with a short latency: a register-fed window makes the warp
+// wait an L2 round trip at EVERY step (the consumer of the word in flight waits for the load another lane issued one
+// step earlier: 64 % of the stall samples, profiles/r02*), and a cp.async ring per lane saturates the MIO queue.  The
+// region stride is 4 words mod 32, so lanes at the same offset of their segments read different banks.
+constexpr int EMIT_TPB = 32;
+constexpr uint32_t EMIT_GUARD = 1536;                                 // bits
+constexpr uint32_t EMIT_REGION = 784;                                 // bytes per lane
+constexpr uint32_t EMIT_UNITS = (15 + SEG_BYTES + EMIT_GUARD / 8 + 31 + 12 + 15) / 16;
+static_assert(EMIT_UNITS * 16 <= EMIT_REGION && EMIT_REGION % 16 == 0 && (EMIT_REGION / 4) % 32 == 4, "emit staging layout");
 
 // Blocks of segment g that exist in its plane (trailing pad bits can look like blocks).
 __device__ __forceinline__ uint32_t seg_blocks(const uint32_t* __restrict__ seg_cnt, uint32_t g, uint32_t first, uint32_t nb) {
@@ -413,58 +429,70 @@ __device__ __forceinline__ uint32_t seg_blocks(const uint32_t* __restrict__ seg_
 }
 
 template <bool FOLD>
-__global__ void __launch_bounds__(EMIT_TPB, 16)
+__global__ void __launch_bounds__(EMIT_TPB, 8)
 k_entropy_emit(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
                const uint32_t* __restrict__ seg_stream, uint32_t seg_lo, uint32_t seg_hi,
                const uint32_t* __restrict__ seg_entry, const uint32_t* __restrict__ seg_cnt,
-               const uint32_t* __restrict__ seg_first, uint32_t* __restrict__ rec, uint16_t* __restrict__ blkrec, uint32_t seg0,
+               const uint32_t* __restrict__ seg_first, uint2* __restrict__ blk_info, uint32_t* __restrict__ rec, uint32_t seg0,
                unsigned long long* __restrict__ n_entries) {
+    __shared__ __align__(16) uint8_t s_bits[EMIT_TPB * EMIT_REGION];
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(s_bits) + threadIdx.x * EMIT_REGION;
     const uint32_t g = seg_lo + blockIdx.x * EMIT_TPB + threadIdx.x;
-    Parser ps;
+    ParserT<FeedSmem> ps;
     ps.init_parked();
-    // The lane writes the record offset of the DC record of each of its cnt blocks AND of the block after them:
-    // blkrec[cnt] is the number of records the segment holds.  bo .. bend = table entries still to write.
-    uint32_t bo = 0, bend = 0, ro = 0;
+    uint32_t kleft = 0, ro = 0, tag = 0;   // blocks still to finish; first record of the region; (block & 31) << 9
+    uint2* bi = nullptr;
     int cur = 0;
     bool iframe = false;
     if (g < seg_hi) {
         const SegCtx c = seg_ctx(payload, streams, seg_stream, g);
         const StreamDesc* sd = streams + c.sid;
-        const uint32_t cnt = seg_blocks(seg_cnt, g, seg_first[g], sd->nb);
-        bo = bend = (g - seg0) * BLK_STRIDE;
-        if (cnt) {
-            ps.start(c.base, seg_entry[g] + c.bias, c.seg_start + SEG_BITS, c.ftotal);
-            bend = bo + cnt + 1u;
+        const uint32_t nb = sd->nb, first = seg_first[g];
+        kleft = seg_blocks(seg_cnt, g, first, nb);
+        // A stream that ends early leaves the remaining blocks empty (zero coefficients).
+        if (c.seg + 1u == sd->nseg)
+            for (uint32_t b = min(first, nb) + kleft; b < nb; b++) blk_info[sd->block_base + b] = make_uint2(BLK_NO_SEG, 0);
+        if (kleft) {
+            const uint8_t* g0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(c.base + (size_t)c.seg * SEG_BYTES) & ~(uintptr_t)15);
+#pragma unroll 1
+            for (uint32_t u = 0; u < EMIT_UNITS; u++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + u * 16u), "l"(g0 + u * 16u) : "memory");
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            ps.start_smem(c.base, seg_entry[g] + c.bias, c.seg_start + SEG_BITS, c.ftotal, g0, s0, EMIT_GUARD);
+            bi = blk_info + sd->block_base + first;
             ro = (g - seg0) * REC_STRIDE;
+            tag = (first & 31u) << 9;
             iframe = sd->ptype == 0;
-        } else {
-            blkrec[bo] = 0;
         }
     }
-    uint32_t o = 0;                      // records so far (warp-uniform)
-    const uint32_t bo0 = bo;
-    while (__any_sync(FULL_MASK, bo != bend)) {
+    uint32_t o = 0, o_blk = 0, written = 0;      // o: records so far (warp-uniform); o_blk: the current block's DC record
+    int level = 0;
+    while (__any_sync(FULL_MASK, kleft != 0u)) {
         uint32_t q[8];
-        const bool wr = bo != bend;
+        const bool wr = kleft != 0u;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            Parser::Sym y;
-            ps.step<true, FOLD>(y);
-            if (y.dc) cur += y.e;        // I frames: the running sum `cur` of lossless_decode.c:94; P frames record the delta (:91)
+            ParserT<FeedSmem>::Sym y;
+            const bool end = ps.step<true, FOLD>(y);
+            if (y.dc) { cur += y.e; level = iframe ? cur : y.e; o_blk = o + j; }   // lossless_decode.c:94 (I) / :91 (P)
             const uint32_t lo = y.dc ? REC_DC : (y.coded ? (y.at >> 24) : REC_NONE);
-            q[j] = lo | ((uint32_t)((y.dc && iframe) ? cur : y.e) << 16);
-            if (y.dc && bo != bend) { asm volatile("st.global.L1::no_allocate.u16 [%0], %1;" ::"l"(blkrec + bo), "h"((uint16_t)(o + j)) : "memory"); bo++; }
+            q[j] = lo | tag | ((uint32_t)y.e << 16);
+            if (end && kleft) {
+                *bi++ = make_uint2(ro + o_blk, ((uint32_t)level & 0xFFFFu) | ((o + j + 1u - o_blk) << 16));
+                tag = (tag + (1u << 9)) & (31u << 9);
+                kleft--;
+                written = o + j + 1u;
+            }
         }
         if (wr) st_global_v8(rec + ro + o, q);
         o += 8u;
-        if (bo == bend) ps.park();       // done (at most 8 steps past its last block: inside the payload's padding)
+        if (kleft == 0u) ps.park();      // done (at most 7 steps past its last block: inside the staged bytes)
         if (o == REC_STRIDE) {           // non-conforming input: the region is full, the rest of the segment is dropped
-            for (; bo != bend; bo++) blkrec[bo] = (uint16_t)o;
+            for (; kleft; kleft--) *bi++ = make_uint2(ro + REC_STRIDE - 1u, 0u);
             break;
         }
     }
     {   // statistics: records written by this launch (one atomic per warp)
-        uint32_t written = bend != bo0 ? blkrec[bend - 1u] : 0u;
 #pragma unroll
         for (int d = 16; d; d >>= 1) written += __shfl_xor_sync(FULL_MASK, written, d);
         if ((threadIdx.x & 31) == 0 && written) atomicAdd(n_entries, (unsigned long long)written);
@@ -472,78 +500,13 @@ k_entropy_emit(const uint8_t* __restrict__ payload, const StreamDesc* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tile descriptors: one thread per segment writes the descriptor of every tile (32 consecutive blocks of the plane)
-// whose FIRST block the segment owns -- every existing block has exactly one owner, so every tile has one writer;
-// the tiles past a stream's last block (a stream that ends early leaves the remaining blocks empty = zero
-// coefficients) are written by the thread of the stream's last segment.  Runs after k_entropy_dcscan: fast.w
-// carries the DC predictors entering the first two runs' segments.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_entropy_tiles(const StreamDesc* __restrict__ streams, const uint32_t* __restrict__ seg_stream, uint32_t seg_lo,
-                uint32_t seg_hi, const uint32_t* __restrict__ seg_cnt, const uint32_t* __restrict__ seg_first,
-                const uint32_t* __restrict__ seg_dc, const uint32_t* __restrict__ seg_nrec,
-                const uint16_t* __restrict__ blkrec, uint32_t seg0, TileDesc* __restrict__ tiles, uint32_t stream0) {
-    const uint32_t g = seg_lo + blockIdx.x * 128u + threadIdx.x;
-    if (g >= seg_hi) return;
-    const uint32_t sid = __ldg(seg_stream + g);
-    const StreamDesc sd = streams[sid];
-    if (g - sd.seg_base >= sd.nseg) return;                           // a padding segment (SUPER alignment)
-    const uint32_t nb = sd.nb, tpp = (nb + 31u) / 32u;
-    TileDesc* td = tiles + (size_t)(sid - stream0) * tpp;
-    const uint32_t g_end = sd.seg_base + sd.nseg;                      // the stream's segments are [seg_base, g_end)
-    auto blocks_of = [&](uint32_t s, uint32_t& first) {
-        first = seg_first[s];
-        return seg_blocks(seg_cnt, s, first, nb);
-    };
-    uint32_t first;
-    const uint32_t cnt = blocks_of(g, first);
-    const uint32_t stop = min(first, nb) + cnt;                        // blocks [first, stop) are this segment's
-    for (uint32_t T = (first + 31u) / 32u; T * 32u < stop; T++) {
-        const uint32_t b0 = T * 32u, b1 = min(b0 + 32u, nb);
-        const uint16_t* br = blkrec + (size_t)(g - seg0) * BLK_STRIDE;
-        const uint32_t r0 = br[b0 - first];
-        TileDesc d;
-        d.fast.x = (g - seg0) * REC_STRIDE + r0;
-        d.fast.w = seg_dc[g];
-        d.fast.y = 0u;
-        d.slow = make_uint4(g + 1u, 1u, 0u, 0u);
-        if (b1 <= stop) {                                              // the tile ends inside this segment
-            d.fast.z = (b1 < stop ? (uint32_t)br[b1 - first] : seg_nrec[g]) - r0;
-        } else {
-            uint32_t n0 = seg_nrec[g] - r0, n1 = 0u, nruns = 1u, nlast = 0u;
-            for (uint32_t s = g + 1u; s < g_end; s++) {               // the following segments of the stream
-                uint32_t f2;
-                const uint32_t c2 = blocks_of(s, f2);
-                nruns++;
-                const bool last = f2 + c2 >= b1 || s + 1u == g_end;
-                const uint32_t n = (c2 && b1 < f2 + c2) ? (uint32_t)blkrec[(size_t)(s - seg0) * BLK_STRIDE + (b1 - f2)]
-                                                         : (c2 ? seg_nrec[s] : 0u);
-                if (s == g + 1u) { n1 = n; d.fast.w |= seg_dc[s] << 16; d.fast.y = (s - seg0) * REC_STRIDE; }
-                if (last) { nlast = n; break; }
-            }
-            d.fast.z = n0 | (n1 << 16);
-            if (nruns > 2u) d.fast.y |= TILE_MORE;
-            d.slow.y = nruns; d.slow.z = nlast;
-        }
-        td[T] = d;
-    }
-    if (g + 1u == g_end) {                                             // tiles without any block
-        TileDesc z;
-        z.fast = make_uint4(0u, 0u, 0u, 0u); z.slow = make_uint4(0u, 0u, 0u, 0u);
-        for (uint32_t T = (stop + 31u) / 32u; T < tpp; T++) td[T] = z;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// DC predictors: one warp per stream.  A segment's DC total is the running sum in the DC record of its last block
+// DC predictors: one warp per stream.  A segment's DC total is the running sum its last block's index entry carries
 // (I frames; P-frame DC symbols are deltas against the previous frame: no predictor); the exclusive prefix sum mod
-// 2^16 of the totals is the value of `cur` (lossless_decode.c:73,94) entering each segment -> seg_dc.  Also copies the
-// segment's record count, blkrec[cnt], to seg_nrec.
+// 2^16 of the totals is the value of `cur` (lossless_decode.c:73,94) entering each segment -> seg_dc.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_entropy_dcscan(const StreamDesc* __restrict__ streams, uint32_t n_streams, const uint32_t* __restrict__ seg_cnt,
-                 const uint32_t* __restrict__ seg_first, const uint32_t* __restrict__ rec, const uint16_t* __restrict__ blkrec,
-                 uint32_t seg0, uint32_t* __restrict__ seg_dc, uint32_t* __restrict__ seg_nrec) {
+                 const uint32_t* __restrict__ seg_first, const uint2* __restrict__ blk_info, uint32_t* __restrict__ seg_dc) {
     const uint32_t s = blockIdx.x * 4u + (threadIdx.x >> 5);
     if (s >= n_streams) return;
     const StreamDesc sd = streams[s];
@@ -552,11 +515,9 @@ k_entropy_dcscan(const StreamDesc* __restrict__ streams, uint32_t n_streams, con
     for (uint32_t i0 = 0; i0 < sd.nseg; i0 += 32) {
         const uint32_t i = i0 + lane, g = sd.seg_base + i;
         uint32_t x = 0;
-        if (i < sd.nseg) {
-            const uint32_t cnt = seg_blocks(seg_cnt, g, seg_first[g], sd.nb);
-            const uint16_t* br = blkrec + (size_t)(g - seg0) * BLK_STRIDE;
-            seg_nrec[g] = br[cnt];
-            if (cnt && sd.ptype == 0) x = rec[(size_t)(g - seg0) * REC_STRIDE + br[cnt - 1u]] >> 16;
+        if (i < sd.nseg && sd.ptype == 0) {
+            const uint32_t first = seg_first[g], cnt = seg_blocks(seg_cnt, g, first, sd.nb);
+            if (cnt) x = blk_info[sd.block_base + first + cnt - 1u].y & 0xFFFFu;
         }
         uint32_t inc = x;
 #pragma unroll
@@ -610,19 +571,16 @@ cudaError_t launch_entropy_emit(const EntropyJob& j, cudaStream_t s) {
     if (j.seg_hi <= j.seg_lo) return cudaSuccess;
     const uint32_t n = j.seg_hi - j.seg_lo;
     const unsigned grid = (n + EMIT_TPB - 1) / EMIT_TPB;
-    if (j.fold_end)
+    if (j.fold_end || getenv("MJ_EMIT_FOLD"))
         k_entropy_emit<true><<<grid, EMIT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry,
-                                                       j.d_seg_cnt, j.d_seg_first, j.d_rec, j.d_blkrec, j.seg0, j.d_fixups + 1);
+                                                       j.d_seg_cnt, j.d_seg_first, j.d_blk_info, j.d_rec, j.seg0, j.d_fixups + 1);
     else
         k_entropy_emit<false><<<grid, EMIT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry,
-                                                        j.d_seg_cnt, j.d_seg_first, j.d_rec, j.d_blkrec, j.seg0, j.d_fixups + 1);
+                                                        j.d_seg_cnt, j.d_seg_first, j.d_blk_info, j.d_rec, j.seg0, j.d_fixups + 1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k_entropy_dcscan<<<(j.n_streams + 3) / 4, 128, 0, s>>>(j.d_streams + j.stream_lo, j.n_streams, j.d_seg_cnt, j.d_seg_first, j.d_rec,
-                                                          j.d_blkrec, j.seg0, j.d_seg_dc, j.d_seg_nrec);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    k_entropy_tiles<<<(n + 127) / 128, 128, 0, s>>>(j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_cnt, j.d_seg_first,
-                                                    j.d_seg_dc, j.d_seg_nrec, j.d_blkrec, j.seg0, j.d_tiles, j.stream_lo);
+    k_entropy_dcscan<<<(j.n_streams + 3) / 4, 128, 0, s>>>(j.d_streams + j.stream_lo, j.n_streams, j.d_seg_cnt, j.d_seg_first,
+                                                          j.d_blk_info, j.d_seg_dc);
     return cudaGetLastError();
 }
 

@@ -149,19 +149,13 @@ void make_chunks(const Plan& plan, uint32_t K, std::vector<Chunk>& chunks, std::
     }
 }
 
-size_t chunk_scratch_bytes(size_t segs, size_t streams, uint32_t nb) {
-    const size_t tpp = (nb + 31u) / 32u;
-    return ((streams * tpp * sizeof(TileDesc) + 255) & ~(size_t)255) + segs * (size_t)REC_STRIDE * 4 +
-           ((segs * (size_t)BLK_STRIDE * 2 + 255) & ~(size_t)255) + 256;
+size_t chunk_scratch_bytes(size_t segs, size_t blocks) {
+    return ((blocks * 8 + 255) & ~(size_t)255) + segs * (size_t)REC_STRIDE * 4 + 256;
 }
-void carve_chunk_scratch(EntropyJob& j, void* base, size_t segs, size_t streams, uint32_t nb) {
-    const size_t tpp = (nb + 31u) / 32u;
+void carve_chunk_scratch(EntropyJob& j, void* base, size_t blocks, size_t first_block) {
     uint8_t* w = static_cast<uint8_t*>(base);
-    j.d_tiles = reinterpret_cast<TileDesc*>(w);
-    w += (streams * tpp * sizeof(TileDesc) + 255) & ~(size_t)255;
-    j.d_rec = reinterpret_cast<uint32_t*>(w);
-    w += segs * (size_t)REC_STRIDE * 4;
-    j.d_blkrec = reinterpret_cast<uint16_t*>(w);
+    j.d_blk_info = reinterpret_cast<uint2*>(w) - first_block;     // StreamDesc.block_base is plan-relative
+    j.d_rec = reinterpret_cast<uint32_t*>(w + ((blocks * 8 + 255) & ~(size_t)255));
 }
 
 }  // namespace mj
@@ -284,7 +278,7 @@ namespace {
 
 struct Tables {           // device addresses inside ctx->tables / ctx->segs
     StreamDesc* streams;
-    uint32_t *seg_stream, *seg_entry, *seg_exit, *seg_cnt, *seg_first, *seg_dc, *seg_nrec, *stream_blocks;
+    uint32_t *seg_stream, *seg_entry, *seg_exit, *seg_cnt, *seg_first, *seg_dc, *stream_blocks;
     unsigned long long* fixups;
 };
 
@@ -302,9 +296,8 @@ Tables tables_of(mjpeg423_b200_ctx* c, const Plan& plan) {
     t.seg_first = reinterpret_cast<uint32_t*>(sb + 3 * b_seg);
     t.seg_dc = reinterpret_cast<uint32_t*>(sb + 4 * b_seg);
     t.seg_stream = reinterpret_cast<uint32_t*>(sb + 5 * b_seg);
-    t.seg_nrec = reinterpret_cast<uint32_t*>(sb + 6 * b_seg);
-    t.stream_blocks = reinterpret_cast<uint32_t*>(sb + 7 * b_seg);
-    t.fixups = reinterpret_cast<unsigned long long*>(sb + 7 * b_seg + b_sb);
+    t.stream_blocks = reinterpret_cast<uint32_t*>(sb + 6 * b_seg);
+    t.fixups = reinterpret_cast<unsigned long long*>(sb + 6 * b_seg + b_sb);
     return t;
 }
 
@@ -313,7 +306,7 @@ int upload_tables(mjpeg423_b200_ctx* c, const Plan& plan, Tables& t, cudaStream_
     int rc = c->tables.reserve(plan.streams.size() * sizeof(StreamDesc) + 256);
     if (rc) return rc;
     const size_t nseg = plan.f_seg0.empty() ? 0 : plan.f_seg0.back();
-    rc = c->segs.reserve(7 * align256(nseg * 4) + align256(plan.streams.size() * 4) + 256);   // ... + 2 x u64 counters
+    rc = c->segs.reserve(6 * align256(nseg * 4) + align256(plan.streams.size() * 4) + 256);   // ... + 2 x u64 counters
     if (rc) return rc;
     t = tables_of(c, plan);
     CU(cudaMemcpyAsync(t.streams, plan.streams.data(), plan.streams.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, s));
@@ -354,10 +347,10 @@ int decode_mode(const mjpeg423_b200_ctx* c, const Plan& plan) {
     return c->staged;
 }
 
-// Per-chunk scratch: tile descriptors + record lists (REC_STRIDE records per segment) + block tables (BLK_STRIDE
-// u16 per segment) and, in the staged modes, coefficient planes.
+// Per-chunk scratch: block index (8 bytes per block) + record lists (REC_STRIDE records per segment) and, in the
+// staged modes, coefficient planes.
 size_t chunk_index_bytes(const Plan& plan, uint32_t f0, uint32_t f1) {
-    return chunk_scratch_bytes(plan.f_seg0[f1] - plan.f_seg0[f0], (size_t)(f1 - f0) * 3, plan.nb);
+    return chunk_scratch_bytes(plan.f_seg0[f1] - plan.f_seg0[f0], (size_t)(f1 - f0) * 3 * plan.nb);
 }
 int reserve_chunk_buffers(mjpeg423_b200_ctx* c, const Plan& plan, const std::vector<Chunk>& chunks, int nbuf) {
     size_t idx_bytes = 0, frames = 0;
@@ -392,9 +385,8 @@ EntropyJob make_job(const Plan& plan, const Tables& t, const uint8_t* d_payload_
     j.d_seg_entry = t.seg_entry; j.d_seg_exit = t.seg_exit; j.d_seg_cnt = t.seg_cnt; j.d_seg_first = t.seg_first;
     j.d_seg_dc = t.seg_dc;
     j.d_stream_blocks = t.stream_blocks; j.d_fixups = t.fixups;
-    j.d_seg_nrec = t.seg_nrec;
     j.seg0 = plan.f_seg0[f0];
-    carve_chunk_scratch(j, d_blkidx, j.seg_hi - j.seg_lo, j.n_streams, plan.nb);
+    carve_chunk_scratch(j, d_blkidx, (size_t)(f1 - f0) * 3 * plan.nb, (size_t)f0 * 3 * plan.nb);
     return j;
 }
 
@@ -416,7 +408,7 @@ int enqueue_chunk(mjpeg423_b200_ctx* c, const Plan& plan, const Tables& t, const
     if (prof) CU(cudaEventRecord(prof[2], s));
     CU(launch_entropy_emit(j, s));
     if (prof) CU(cudaEventRecord(prof[3], s));
-    c->stats.kernel_launches += synced ? 3 : 5;       // emit + DC scan + tile descriptors (+ sync + chain)
+    c->stats.kernel_launches += synced ? 2 : 4;       // emit + DC scan (+ sync + chain)
     if (mode == 0) {
         const uint32_t* d_gops = nullptr;
         if (plan.n_pframes) {                    // GOP-walking variant; its scratch belongs to this chunk buffer
@@ -523,9 +515,9 @@ extern "C" int mjpeg423_b200_decode_resident(mjpeg423_b200_ctx* c, void* d_out) 
     if (plan.n == 0) return MJPEG423_OK;
     if (!d_out) return MJPEG423_E_ARG;
     Tables t = tables_of(c, plan);
-    // chunk size: bounded scratch (records + block tables + tile descriptors, + 128 B/block of coefficients and 64 of
-    // samples in the staged modes)
-    const size_t scratch_frame = chunk_scratch_bytes(plan.f_seg0.back() / plan.n + 1, 3, plan.nb) +
+    // chunk size: bounded scratch (records + block index, + 128 B/block of coefficients and 64 of samples in the
+    // staged modes)
+    const size_t scratch_frame = chunk_scratch_bytes(plan.f_seg0.back() / plan.n + 1, (size_t)3 * plan.nb) +
                                  (size_t)3 * plan.nb * (decode_mode(c, plan) == 2 ? 192 : decode_mode(c, plan) ? 128 : 0);
     const uint32_t K = c->chunk_frames ? std::min(c->chunk_frames, plan.n) : auto_chunk(plan, (uint64_t)4 << 30, scratch_frame);
     int rc = prepare_chunks(c, plan, K, c->s_compute);
@@ -615,7 +607,7 @@ extern "C" int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* c, int16_t* d_c
         c->stats.kernel_launches += 1;
     }
     CU(cudaEventRecord(e[4], s));
-    c->stats.kernel_launches += 5;
+    c->stats.kernel_launches += 4;
     rc = finish_stats(c, plan, t, s);
     CU(cudaEventElapsedTime(&c->stats.total_ms, e[0], e[4]));
     CU(cudaEventElapsedTime(&c->stats.sync_ms, e[0], e[1]));

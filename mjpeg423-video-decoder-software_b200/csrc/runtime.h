@@ -27,26 +27,25 @@ struct EntropyJob {
     uint32_t* d_seg_dc = nullptr;                // plan-wide: DC total, then DC predictor, of every segment
     uint32_t* d_stream_blocks = nullptr;         // plan-wide, per stream
     unsigned long long* d_fixups = nullptr;
-    uint32_t* d_seg_nrec = nullptr;              // plan-wide: records written for every segment
-    // chunk scratch (see common.cuh): segment g's records start at (g - seg0) * REC_STRIDE, its block table at
-    // (g - seg0) * BLK_STRIDE; the tile descriptors of stream s start at (s - stream_lo) * tiles per plane
+    // chunk scratch (see common.cuh): the block index is addressed by StreamDesc.block_base + b, segment g's records
+    // start at (g - seg0) * REC_STRIDE
+    uint2* d_blk_info = nullptr;
     uint32_t* d_rec = nullptr;
-    uint16_t* d_blkrec = nullptr;
-    TileDesc* d_tiles = nullptr;
     uint32_t seg0 = 0;
 };
 
 cudaError_t launch_seg_stream(const StreamDesc* d_streams, uint32_t n_streams, uint32_t* d_seg_stream, cudaStream_t s);
 cudaError_t launch_entropy_sync(const EntropyJob& j, cudaStream_t s);
 cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s);
-cudaError_t launch_entropy_emit(const EntropyJob& j, cudaStream_t s);    // + DC scan + tile descriptors
+cudaError_t launch_entropy_emit(const EntropyJob& j, cudaStream_t s);    // + DC scan
 cudaError_t launch_decode_coef(const EntropyJob& j, const uint32_t* d_stream_ids, uint32_t n_ids, uint32_t nb,
                                const int16_t* d_quant, int16_t* d_coef, cudaStream_t s);
 // d_gop_first == nullptr: intra-only range.  Otherwise d_gop_first[0 .. n_gops] = chunk-relative first frames of the
 // range's GOPs (+ its end) and d_state = FUSED_STATE_BYTES of scratch that no other launch in flight uses.
-// Bytes of chunk scratch for `segs` segments and `streams` plane streams of `nb` blocks (EntropyJob::d_tiles/d_rec/d_blkrec).
-size_t chunk_scratch_bytes(size_t segs, size_t streams, uint32_t nb);
-void carve_chunk_scratch(EntropyJob& j, void* base, size_t segs, size_t streams, uint32_t nb);
+// Bytes of chunk scratch for `segs` segments and `blocks` blocks (EntropyJob::d_blk_info / d_rec); carve() points the job
+// at it (first_block = the plan-relative index of the chunk's first block).
+size_t chunk_scratch_bytes(size_t segs, size_t blocks);
+void carve_chunk_scratch(EntropyJob& j, void* base, size_t blocks, size_t first_block);
 constexpr int FUSED_MAX_CTAS = 192;                                     // persistent grid: one CTA per SM, at most this many
 constexpr size_t FUSED_STATE_BYTES = (size_t)FUSED_MAX_CTAS * 18 * 3 * 8 * 32 * 16;   // 12 KB per warp
 cudaError_t launch_decode_fused(const EntropyJob& j, const int16_t* d_quant, void* d_out, uint32_t n_frames,
