@@ -58,17 +58,17 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     sd.block_base = 0; sd.prev_base = 0; sd.quant_id = 0; sd.ptype = P ? 1 : 0;   // P: accumulate in place
     const size_t coef_bytes = (size_t)num_blocks * 128;
     int rc;
-    if ((rc = s_in.reserve(len + PAYLOAD_PAD))) return rc;
+    if ((rc = s_in.reserve(len + 64))) return rc;
     if ((rc = s_tab.reserve(256 + 256))) return rc;
     const uint32_t nseg_pad = (sd.nseg + SUPER - 1) / SUPER * SUPER;      // global segment numbering is SUPER-aligned
-    if ((rc = s_seg.reserve((size_t)nseg_pad * 28 + 96))) return rc;
-    if ((rc = s_idx.reserve(chunk_scratch_bytes(nseg_pad, (size_t)num_blocks)))) return rc;
+    if ((rc = s_seg.reserve((size_t)nseg_pad * 24 + 96))) return rc;
+    if ((rc = s_idx.reserve((size_t)num_blocks * 8 + (size_t)nseg_pad * SYM_STRIDE * 4 + 128))) return rc;
     if ((rc = s_mid.reserve(coef_bytes))) return rc;
     uint8_t* tab = s_tab.as<uint8_t>();
     int16_t* d_q = reinterpret_cast<int16_t*>(tab);                  // 128 int16 (table 0 used)
     StreamDesc* d_sd = reinterpret_cast<StreamDesc*>(tab + 256);
     CUX(cudaMemcpyAsync(s_in.p, bitstream, len, cudaMemcpyHostToDevice, s));
-    CUX(cudaMemsetAsync(s_in.as<uint8_t>() + len, 0, PAYLOAD_PAD, s));
+    CUX(cudaMemsetAsync(s_in.as<uint8_t>() + len, 0, 64, s));
     CUX(cudaMemcpyAsync(d_q, quant, 128, cudaMemcpyHostToDevice, s));
     CUX(cudaMemcpyAsync(d_sd, &sd, sizeof(sd), cudaMemcpyHostToDevice, s));
     if (P) CUX(cudaMemcpyAsync(s_mid.p, DCACq, coef_bytes, cudaMemcpyHostToDevice, s));   // in/out state
@@ -86,14 +86,15 @@ int single_stream_decode(mjpeg423_b200_ctx* c, int num_blocks, const void* bitst
     j.d_seg_dc = seg + 4 * (size_t)nseg_pad;
     j.d_stream_blocks = seg + 6 * (size_t)nseg_pad;
     j.d_fixups = reinterpret_cast<unsigned long long*>(seg + ((6 * (size_t)nseg_pad + 3) & ~(size_t)1));
-    j.seg0 = 0;
-    carve_chunk_scratch(j, s_idx.p, (size_t)num_blocks, 0);
+    j.d_blk_info = s_idx.as<uint2>();
+    j.d_sym = s_idx.as<uint32_t>() + ((2 * (size_t)num_blocks + 7) & ~(size_t)7);
+    j.sym_seg0 = 0;
     uint32_t* d_ids = reinterpret_cast<uint32_t*>(tab + 256 + 128);     // one id: stream 0
     CUX(cudaMemsetAsync(d_ids, 0, 4, s));
     CUX(cudaMemsetAsync(j.d_fixups, 0, 16, s));
     CUX(launch_entropy_sync(j, s));
     CUX(launch_entropy_chain(j, s));
-    CUX(launch_entropy_emit(j, s));
+    CUX(launch_entropy_index(j, s));
     CUX(launch_decode_coef(j, d_ids, 1, sd.nb, d_q, s_mid.as<int16_t>(), s));
     CUX(cudaMemcpyAsync(DCACq, s_mid.p, coef_bytes, cudaMemcpyDeviceToHost, s));
     CUX(cudaStreamSynchronize(s));

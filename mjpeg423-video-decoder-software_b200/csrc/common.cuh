@@ -24,24 +24,13 @@ constexpr int MIN_BLOCK_BITS = 12;             // DC size 0 + END (SURVEY.md A.6
 constexpr uint32_t RUNAWAY_BITS = 8192;        // parse guard for non-conforming / speculative garbage
 constexpr uint32_t MAX_STREAM_BYTES = 1u << 28; // bit positions are 32-bit
 constexpr uint32_t MAX_PLANE_BLOCKS = 1u << 24; // blocks per plane (W/8 * H/8): 32768 x 32768 pixels
-// Record lists: the emit pass (k_entropy_emit) writes ONE 32-bit record per symbol step of a segment's blocks into a
-// fixed-stride region (the steps of the lanes of a warp are synchronous, so the record position is the step count:
-// no compaction, no per-lane queue, eight records leave as one 32-byte store):
-//     bits 0..7    zig-zag index of a coded AC coefficient (1..63); 0 in a DC record; 255 = the step carried no
-//                  coefficient (ZRL, a stand-alone END); other values >= 64 = non-conforming input, ignored
-//     bit 8        set for a block's DC symbol
-//     bits 9..13   (index of the block in its plane) & 31: the lane that owns the block in the decode kernels' warp
-//                  tiles of 32 consecutive blocks
-//     bits 16..31  AC: amplitude (HUFF_EXTEND, LIB/decoder/lossless_decode.c:204); DC: see BlockInfo
-// A conforming segment takes at most SEG_BITS / 6 steps that start inside it (DC size 0 + stand-alone END = two
-// steps per 12 bits) plus the rest of its last block (<= 68 steps): 751.
-constexpr uint32_t REC_STRIDE = 768;            // records per segment region, a multiple of 8 (32-byte sector stores)
-constexpr uint32_t REC_DC = 0x100u, REC_NONE = 0xFFu;
-// The record carries a coded AC coefficient with a conforming index.
-__device__ __forceinline__ bool rec_is_ac(uint32_t e) { return ((e & 0xFFu) - 1u) < 63u; }
-// Block index entry (uint2): .x = position of the block's first record (its DC record) -- always inside its segment's
-// region, so .x / REC_STRIDE names the segment (whose DC predictor the decode kernels add) -- or BLK_NO_SEG for a block
-// the stream does not hold; .y = segment-relative DC level | records of the block << 16.
+// Symbol list: the index pass writes every coded AC coefficient of a segment's blocks as one 32-bit entry
+// (zig-zag index | amplitude << 16) into a fixed-stride region.  A segment owns at most SEG_BITS/9 coded
+// symbols (>= 9 bits each) that start inside it plus the rest of its last block (<= 63 AC coefficients).
+constexpr uint32_t SYM_STRIDE = (SEG_BYTES * 8 / 9 + 63 + 7) / 8 * 8;   // entries per segment, a multiple of 8
+// Block index entry (uint2): .x = position of the block's first list entry -- always inside its segment's
+// region, so .x / SYM_STRIDE names the segment (whose DC predictor the decode kernels add) -- or BLK_NO_SEG
+// for a block the stream does not hold; .y = segment-relative DC level | list entries << 16.
 constexpr uint32_t BLK_NO_SEG = 0xFFFFFFFFu;
 
 // One plane bitstream of one frame (built by the host from the 16-byte frame headers,
@@ -78,92 +67,18 @@ struct StreamDesc {
 // (w0 = current, w1 = next).  Positions are counted from the ALIGNED word that holds the stream's first
 // byte ("f" positions = stream bit position + bias, bias = 8 * (address & 3)), so the offset into w0 is
 // simply fpos & 31: the next 32 stream bits are ONE funnel shift (which takes its amount mod 32) and a
-// word crossing is bit 5 of fpos flipping.  The words behind the window come from a Feed (below).  The payload
-// buffer is padded by PAYLOAD_PAD bytes: reads a few words past any stream end are in bounds.
+// word crossing is bit 5 of fpos flipping.  A third word w2 is in flight behind them: the funnel shift reads
+// w1 in EVERY step, so a word loaded straight into w1 would be waited for one step later; loaded into w2 it
+// is not touched until the next crossing (3-4 symbols), which hides an L2 round trip.  The payload buffer
+// is padded: reads up to 16 bytes past any stream end are in bounds.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t stream_bias(const uint8_t* base) {
     return (uint32_t)(reinterpret_cast<uintptr_t>(base) & 3u) * 8u;
 }
 
-// Where the parser's bitstream words come from.  take() is called when the window crosses into its second word: it
-// returns the next window word (big-endian) and requests the one after the word in flight.
-//
-// FeedReg: the word in flight lives in a register (w2), requested with a plain load.  Simple, but the hardware
-// tracks register loads per warp: the PRMT that consumes w2 at a crossing waits for the load ANOTHER lane issued one
-// step earlier, so a warp makes one step per L2 round trip unless other warps cover it (fine for short or rare
-// passes: the chain kernel).
-struct FeedReg {
+struct Parser {
     const uint32_t* wp;    // next aligned word to fetch
-    uint32_t w2;           // word in flight (raw: byte-swapped when it moves into the window)
-    __device__ __forceinline__ void start(const uint32_t* w) { w2 = __ldg(w + 2); wp = w + 3; }
-    __device__ __forceinline__ void init_parked() { wp = nullptr; w2 = 0u; }
-    __device__ __forceinline__ uint32_t take() {
-        const uint32_t r = __byte_perm(w2, 0, 0x0123);
-        w2 = __ldg(wp);
-        wp++;
-        return r;
-    }
-};
-// FeedRing<T>: the words in flight live in a per-lane ring of RING_WORDS words in shared memory (slot s of thread t at
-// ring + (s * T + t) * 4: conflict-free), filled with cp.async SIXTEEN words ahead of the one the window takes next.
-// cp.async has no destination register, so nothing waits for a request until the pass says so: ONE
-// cp.async.wait_all per group of 8 steps (a lane crosses at most 8 words in 8 steps, and a word is requested at
-// least 9 crossings before it is read, so a wait lies between every request and its read).  The ring of a CTA must
-// be aligned to its size (the slot address wraps with one LOP3).  Reads run up to 19 words past the window: the
-// payload buffer is padded by PAYLOAD_PAD bytes.
-constexpr int RING_WORDS = 32;
-constexpr size_t PAYLOAD_PAD = 320;
-template <int T>
-struct FeedRing {
-    static constexpr uint32_t STRIDE = T * 4u, BYTES = RING_WORDS * STRIDE;
-    uint32_t ra;           // shared address of the slot the next take() reads
-    const uint32_t* gp;    // global word the next take() requests (it goes to slot + 16)
-    uint32_t w2;           // look-ahead word (raw), read from the ring at the previous crossing
-    // ring_t = shared address of slot 0 of this thread
-    __device__ __forceinline__ void start(const uint32_t* w, uint32_t ring_t) {
-        w2 = __ldg(w + 2);
-        ra = ring_t;
-#pragma unroll
-        for (int k = 0; k < 16; k++)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_t + k * STRIDE), "l"(w + 3 + k) : "memory");
-        gp = w + 19;
-    }
-    __device__ __forceinline__ void init_parked(uint32_t ring_t) { ra = ring_t; gp = nullptr; w2 = 0u; }
-    __device__ __forceinline__ uint32_t take() {
-        const uint32_t r = __byte_perm(w2, 0, 0x0123);
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(ra) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ra ^ (16u * STRIDE)), "l"(gp) : "memory");
-        gp++;
-        ra = (ra & ~(BYTES - 1u)) | ((ra + STRIDE) & (BYTES - 1u));
-        return r;
-    }
-    static __device__ __forceinline__ void wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-};
-
-// FeedSmem: the pass has copied the bytes the lane can reach into shared memory up front (k_entropy_emit: a segment
-// plus the longest block that can hang over its end); the window words are plain LDS, whose latency is short enough
-// for the per-step wait to be hidden by one or two other warps.
-struct FeedSmem {
-    uint32_t wa;           // shared address of the next word to take
-    uint32_t w2;           // look-ahead word (raw)
-    __device__ __forceinline__ uint32_t lds(uint32_t a) const {
-        uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-        return v;
-    }
-    __device__ __forceinline__ void init_parked() { wa = 0u; w2 = 0u; }
-    __device__ __forceinline__ uint32_t take() {
-        const uint32_t r = __byte_perm(w2, 0, 0x0123);
-        w2 = lds(wa);
-        wa += 4u;
-        return r;
-    }
-};
-
-template <class Feed>
-struct ParserT {
-    Feed fd;
-    uint32_t w0, w1;       // current word, look-ahead word; MSB first
+    uint32_t w0, w1, w2;   // current word, look-ahead word, word in flight; MSB first
     uint32_t fpos;         // f position of the next symbol
     uint32_t flim;         // a block is ended at or after this f position (see above)
     uint32_t idx;          // zig-zag index of the next AC coefficient << 24 (the add wraps at 8 bits like the reference's
@@ -173,30 +88,14 @@ struct ParserT {
 
     // fbits = f position to start at (a block start), job_end = f position where the caller's job ends (it stops at
     // the first block start at or after it), ftotal = f position of the end of the stream.
-    template <class... A>
-    __device__ __forceinline__ void start(const uint8_t* base, uint32_t fbits, uint32_t job_end, uint32_t ftotal, A... feed_args) {
+    __device__ __forceinline__ void start(const uint8_t* base, uint32_t fbits, uint32_t job_end, uint32_t ftotal) {
         const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)3) + (fbits >> 5);
         w0 = __byte_perm(__ldg(w), 0, 0x0123);
         w1 = __byte_perm(__ldg(w + 1), 0, 0x0123);
-        fd.start(w, feed_args...);
+        w2 = __ldg(w + 2);                               // kept raw: byte-swapped when it moves into w1
+        wp = w + 3;
         fpos = fbits;
         flim = min(job_end + RUNAWAY_BITS, ftotal);
-        idx = 1u << 24;
-        nh = (uint32_t)-4;
-        rmask = 32u;
-    }
-    // FeedSmem only: the stream bytes from the aligned global address g0 on sit at shared address s0; a block is ended
-    // `guard` bits behind the job at the latest (the staged bytes end there).
-    __device__ __forceinline__ void start_smem(const uint8_t* base, uint32_t fbits, uint32_t job_end, uint32_t ftotal,
-                                               const uint8_t* g0, uint32_t s0, uint32_t guard) {
-        const uintptr_t w = (reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)3) + (size_t)(fbits >> 5) * 4u;
-        const uint32_t sw = s0 + (uint32_t)(w - reinterpret_cast<uintptr_t>(g0));
-        w0 = __byte_perm(fd.lds(sw), 0, 0x0123);
-        w1 = __byte_perm(fd.lds(sw + 4u), 0, 0x0123);
-        fd.w2 = fd.lds(sw + 8u);
-        fd.wa = sw + 12u;
-        fpos = fbits;
-        flim = min(job_end + guard, ftotal);
         idx = 1u << 24;
         nh = (uint32_t)-4;
         rmask = 32u;
@@ -206,10 +105,8 @@ struct ParserT {
     // window (DC size 0 / END symbols: no coefficient, 4 or 8 bits each) without ever touching memory again,
     // and the pass ignores what it returns.
     __device__ __forceinline__ void park() { rmask = 0u; w0 = 0u; w1 = 0u; }
-    template <class... A>
-    __device__ __forceinline__ void init_parked(A... feed_args) {
-        fd.init_parked(feed_args...);
-        w0 = w1 = 0u; fpos = 0u; flim = 0u; idx = 1u << 24; nh = (uint32_t)-4; rmask = 0u;
+    __device__ __forceinline__ void init_parked() {
+        wp = nullptr; w0 = w1 = w2 = 0u; fpos = 0u; flim = 0u; idx = 1u << 24; nh = (uint32_t)-4; rmask = 0u;
     }
 
     // What the last step() consumed.
@@ -248,9 +145,11 @@ struct ParserT {
         const bool end0 = (!szd && run != 15u) || (coded && at >= (63u << 24));   // END / coefficient 63
         const bool end_next = FOLD_END && !end0 && ((t << len) >> 24) == 0u;   // ... or an END right behind this symbol
         const uint32_t fnew = fpos + len + (end_next ? 8u : 0u);        // <= 31 bits: at most one word crossing
-        if ((fpos ^ fnew) & rmask) {                                    // crossed into w1: take the next word
+        if ((fpos ^ fnew) & rmask) {                                    // crossed into w1: fetch the word after w2
             w0 = w1;
-            w1 = fd.take();
+            w1 = __byte_perm(w2, 0, 0x0123);
+            w2 = __ldg(wp);
+            wp++;
         }
         const bool end = end0 || end_next || fnew >= flim;              // ... or the guard
         idx = end ? (1u << 24) : at + (coded ? (1u << 24) : 0u);
@@ -262,7 +161,6 @@ struct ParserT {
         return end;
     }
 };
-using Parser = ParserT<FeedReg>;
 
 constexpr uint32_t FULL_MASK = 0xFFFFFFFFu;
 
@@ -386,7 +284,7 @@ __device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_syn
 
 // 256-bit global store (sm_100+): one full 32-byte sector per lane.
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
-    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
                  "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }

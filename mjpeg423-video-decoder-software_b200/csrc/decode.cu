@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_slot_rows(const uint8_t* smem, int t, uint4
 // Block index entry -> .y with the DC level made absolute: adds the DC predictor entering the block's segment
 // (k_entropy_dcscan; zero for P frames, whose DC symbols are deltas against the previous frame).
 __device__ __forceinline__ uint32_t absolute_dc(uint2 info, const uint32_t* __restrict__ seg_dc) {
-    const uint32_t pred = info.x == BLK_NO_SEG ? 0u : __ldg(seg_dc + info.x / REC_STRIDE);
+    const uint32_t pred = info.x == BLK_NO_SEG ? 0u : __ldg(seg_dc + info.x / SYM_STRIDE);
     return (info.y & 0xFFFF0000u) | ((info.y + pred) & 0xFFFFu);
 }
 
@@ -98,7 +98,6 @@ k_decode_coef(const StreamDesc* __restrict__ streams, const uint32_t* __restrict
         else *d0 = (int16_t)(dc * q0);                                   // :94-95 (dc = running sum `cur`)
         for (uint32_t i = 0; i < n; i++) {
             const uint32_t ent = __ldg(src + i);
-            if (!rec_is_ac(ent)) continue;                                   // the DC record / ZRL / END steps
             const uint32_t z = s_zq[ent & 63u];
             int16_t* d = reinterpret_cast<int16_t*>(slots + slot_off(t, z & 0xFFFFu));
             const int v = ((int)ent >> 16) * (int)(z >> 16);
@@ -229,14 +228,14 @@ k_decode_fused(const uint2* __restrict__ blk_info,
     auto prefetch_lists = [&]() {
 #pragma unroll
         for (int p = 0; p < 3; p++) {
-            npred[p] = infoA[p].x == BLK_NO_SEG ? 0u : __ldg(seg_dc + infoA[p].x / REC_STRIDE);   // DC predictor of the block's segment
+            npred[p] = infoA[p].x == BLK_NO_SEG ? 0u : __ldg(seg_dc + infoA[p].x / SYM_STRIDE);   // DC predictor of the block's segment
             if (p == 0) {
 #pragma unroll
                 for (int i = 0; i < PRE_Y; i++) npreY[i] = 0u;
             } else {
                 npreC[p - 1] = 0u;
             }
-            if (!__any_sync(FULL_MASK, (infoA[p].y >> 16) > 1u)) continue;    // a plane with DC records only (flat chrominance)
+            if (!__any_sync(FULL_MASK, (infoA[p].y >> 16) != 0u)) continue;   // a plane without any entry (flat chrominance)
             uint32_t r0, n1, s0, n2, rest;
             runs(infoA[p].x, infoA[p].x + (infoA[p].y >> 16), r0, n1, s0, n2, rest);
             const uint32_t d2 = s0 - n1 - r0;                            // slot v of the second run is entry r0 + d2 + v
@@ -318,7 +317,7 @@ k_decode_fused(const uint2* __restrict__ blk_info,
             // static background is coded as): the pixels are the previous frame's, which this lane wrote itself.
             bool same = true;
 #pragma unroll
-            for (int p = 0; p < 3; p++) same = same && lxe[p] - lx[p] <= 1u && (meta[p] & 0xFFFFu) == 0u;
+            for (int p = 0; p < 3; p++) same = same && lx[p] == lxe[p] && (meta[p] & 0xFFFFu) == 0u;
             if (__all_sync(FULL_MASK, same)) {
                 if (live) {
                     const uint8_t* prev = dst - (size_t)nb * 256;
@@ -384,7 +383,7 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                 }
             };
             uint32_t m_all = macc;                                        // column 0 always holds the DC coefficient
-            const bool has_ac = __any_sync(FULL_MASK, xe - x > 1u);           // (every block has its DC record; END may be folded into it)
+            const bool has_ac = __any_sync(FULL_MASK, xe != x);
             if (has_ac || has_state) {                                    // (no AC entry in the whole tile: nothing to scatter)
                 // ---- scatter this plane's blocks into the transposed coefficient slots: zeroed (the memset of :77-78)
                 // or, for a P frame, holding the previous frame's coefficients --------------------------------------
@@ -406,9 +405,8 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                 // the tile, no load depends on another.
                 uint32_t m_bits = 1u;
                 auto put = [&](uint32_t ent) {                            // dequantise + scatter one entry (:125)
-                    if (!rec_is_ac(ent)) return;                          // the DC record (its level is in the index) / ZRL / END
                     const uint2 z = zq[ent & 63u];
-                    int16_t* d = reinterpret_cast<int16_t*>(warp_coef + ((ent >> 5) & 0x1F0u) + (z.x & 0xFFFFu));
+                    int16_t* d = reinterpret_cast<int16_t*>(warp_coef + ((ent >> 2) & 0x1F0u) + (z.x & 0xFFFFu));
                     const int v = ((int)ent >> 16) * (int)(z.x >> 16);
                     if (PF) *d = (int16_t)(v + (cur_first ? 0 : (int)*d));   // :122 (P frame: added) / :125 (I frame: stored)
                     else *d = (int16_t)v;
@@ -528,7 +526,7 @@ cudaError_t launch_decode_coef(const EntropyJob& j, const uint32_t* d_stream_ids
                                const int16_t* d_quant, int16_t* d_coef, cudaStream_t s) {
     if (n_ids == 0 || nb == 0) return cudaSuccess;
     dim3 grid((nb + DEC_TPB - 1) / DEC_TPB, n_ids);
-    k_decode_coef<<<grid, DEC_TPB, 0, s>>>(j.d_streams, d_stream_ids, j.d_blk_info, j.d_rec, j.d_seg_dc + j.seg0,
+    k_decode_coef<<<grid, DEC_TPB, 0, s>>>(j.d_streams, d_stream_ids, j.d_blk_info, j.d_sym, j.d_seg_dc + j.sym_seg0,
                                            d_quant, d_coef);
     return cudaGetLastError();
 }
@@ -556,10 +554,10 @@ cudaError_t launch_decode_fused(const EntropyJob& j, const int16_t* d_quant, voi
     const unsigned grid = (unsigned)(want < (uint64_t)n_sm[dev] ? want : (uint64_t)n_sm[dev]);   // persistent: one CTA per SM
     const uint2* bi = j.d_blk_info + (size_t)j.stream_lo * nb;
     if (d_gop_first)
-        k_decode_fused<true><<<grid, FUSED_TPB, FUSED_SMEM, s>>>(bi, j.d_rec, j.d_seg_dc + j.seg0, d_quant, (uint8_t*)d_out, nb, wb,
+        k_decode_fused<true><<<grid, FUSED_TPB, FUSED_SMEM, s>>>(bi, j.d_sym, j.d_seg_dc + j.sym_seg0, d_quant, (uint8_t*)d_out, nb, wb,
                                                                  W, n_frames, d_gop_first, n_gops, (uint4*)d_state);
     else
-        k_decode_fused<false><<<grid, FUSED_TPB, FUSED_SMEM, s>>>(bi, j.d_rec, j.d_seg_dc + j.seg0, d_quant, (uint8_t*)d_out, nb, wb,
+        k_decode_fused<false><<<grid, FUSED_TPB, FUSED_SMEM, s>>>(bi, j.d_sym, j.d_seg_dc + j.sym_seg0, d_quant, (uint8_t*)d_out, nb, wb,
                                                                   W, n_frames, nullptr, 0u, nullptr);
     return cudaGetLastError();
 }

@@ -25,8 +25,6 @@
 // Every pass advances with Parser::step() (common.cuh) in a UNIFORM loop: one step per iteration for
 // every lane, DC/AC and block-end handling predicated, the rare events (checkpoint, end of a job) in a
 // short divergent branch; a lane without work is parked.  Load balance comes from many small CTAs.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "runtime.h"
 
@@ -396,136 +394,142 @@ k_entropy_chain(const uint8_t* __restrict__ payload, const StreamDesc* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// Record lists + block index.  Walking its blocks from the exact state, a segment's lane writes
-//   rec[seg * REC_STRIDE + step]     one record per symbol step (layout: common.cuh); the lanes of a warp step in
-//                                    lock-step from step 0, so the record position is warp-uniform and eight
-//                                    consecutive records leave as ONE 32-byte sector store, straight from the
-//                                    registers the unrolled steps produced them in;
-//   blk_info[block].x                index of the block's first record (its DC record; always inside the segment's
-//                                    region, so x / REC_STRIDE identifies the segment), or BLK_NO_SEG for a block the
-//                                    stream does not hold
-//   blk_info[block].y                DC level relative to the segment's entry (I frames: the int16 running sum `cur`
-//                                    of LIB/decoder/lossless_decode.c:73,94 restarted at 0; P frames: the DC delta
-//                                    itself, :91) | records of the block << 16
-// After this pass no kernel touches the bitstream again: the block-parallel decode kernels (decode.cu) read the
-// records with independent, look-ahead loads instead of a bit-serial dependent chain.
+// Block index + symbol lists.  Walking its blocks from the exact state, a segment's thread writes
+//   sym[seg * SYM_STRIDE + ...]  one entry per coded AC coefficient: zig-zag index | (block index & 31) << 6 |
+//                                amplitude << 16 (the block bits name the lane that owns the block in
+//                                k_decode_fused's warp tiles of 32 consecutive blocks)
+//   blk_info[block].x            index of the block's first entry in sym[] (always inside the segment's region,
+//                                so x / SYM_STRIDE identifies the segment), or BLK_NO_SEG for a block the stream
+//                                does not hold
+//   blk_info[block].y            DC level relative to the segment's entry (I frames: the int16 running sum `cur`
+//                                of LIB/decoder/lossless_decode.c:73,94 restarted at 0; P frames: the DC delta
+//                                itself, :91) | entries << 16
+//   seg_dc[segment]              I frames: sum of the segment's DC deltas (mod 2^16); P frames: 0
+// After this pass no kernel touches the bitstream again: the block-parallel decode kernels (decode.cu)
+// read the lists with independent, look-ahead loads instead of a bit-serial dependent chain.
 // ------------------------------------------------------------------------------------------------
-// One warp per CTA, one segment per lane.  Every lane first copies the bytes its parse can reach into its own
-// shared-memory region (16-byte cp.async): the segment, the longest block the reference decoder accepts hanging over its
-// end (19 + 63 x 23 = 1468 bits; EMIT_GUARD bits are allowed), the <= 7 steps a lane runs on after its last block, and
-// the window look-ahead.  The window words are then LDS with a short latency: a register-fed window makes the warp
-// wait an L2 round trip at EVERY step (the consumer of the word in flight waits for the load another lane issued one
-// step earlier: 64 % of the stall samples, profiles/r02*), and a cp.async ring per lane saturates the MIO queue.  The
-// region stride is 4 words mod 32, so lanes at the same offset of their segments read different banks.
-constexpr int EMIT_TPB = 32;
-constexpr uint32_t EMIT_GUARD = 1536;                                 // bits
-constexpr uint32_t EMIT_REGION = 784;                                 // bytes per lane
-constexpr uint32_t EMIT_UNITS = (15 + SEG_BYTES + EMIT_GUARD / 8 + 31 + 12 + 15) / 16;
-static_assert(EMIT_UNITS * 16 <= EMIT_REGION && EMIT_REGION % 16 == 0 && (EMIT_REGION / 4) % 32 == 4, "emit staging layout");
-
-// Blocks of segment g that exist in its plane (trailing pad bits can look like blocks).
-__device__ __forceinline__ uint32_t seg_blocks(const uint32_t* __restrict__ seg_cnt, uint32_t g, uint32_t first, uint32_t nb) {
-    return first >= nb ? 0u : min(seg_cnt[g], nb - first);
-}
+// Small CTAs, one segment per lane: measured best (3.75 ms / 2000 frames at 1080p; pools of 2 / 4 / 8 segments per
+// lane pulled from the CTA-wide counter: 4.0 / 4.45 / 4.8 ms) -- the hardware CTA scheduler balances many short CTAs
+// better than lanes balance inside a long-lived one.  The pull loop below stays general (INDEX_SLOTS >= INDEX_TPB).
+constexpr int INDEX_TPB = 64;
+constexpr int INDEX_SLOTS = 64;      // segments per CTA
 
 template <bool FOLD>
-__global__ void __launch_bounds__(EMIT_TPB, 8)
-k_entropy_emit(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
-               const uint32_t* __restrict__ seg_stream, uint32_t seg_lo, uint32_t seg_hi,
-               const uint32_t* __restrict__ seg_entry, const uint32_t* __restrict__ seg_cnt,
-               const uint32_t* __restrict__ seg_first, uint2* __restrict__ blk_info, uint32_t* __restrict__ rec, uint32_t seg0,
-               unsigned long long* __restrict__ n_entries) {
-    __shared__ __align__(16) uint8_t s_bits[EMIT_TPB * EMIT_REGION];
-    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(s_bits) + threadIdx.x * EMIT_REGION;
-    const uint32_t g = seg_lo + blockIdx.x * EMIT_TPB + threadIdx.x;
-    ParserT<FeedSmem> ps;
+__global__ void __launch_bounds__(INDEX_TPB, 16)
+k_entropy_index(const uint8_t* __restrict__ payload, const StreamDesc* __restrict__ streams,
+                const uint32_t* __restrict__ seg_stream, uint32_t seg_lo, uint32_t seg_hi,
+                const uint32_t* __restrict__ seg_entry, const uint32_t* __restrict__ seg_cnt,
+                const uint32_t* __restrict__ seg_first, uint32_t* __restrict__ seg_dc, uint2* __restrict__ blk_info,
+                uint32_t* __restrict__ sym, uint32_t sym_seg0, unsigned long long* __restrict__ n_entries) {
+    __shared__ uint32_t s_next;
+    const int t = threadIdx.x;
+    const uint32_t g0 = seg_lo + blockIdx.x * INDEX_SLOTS;
+    const uint32_t k_hi = min((uint32_t)INDEX_SLOTS, seg_hi - g0);
+    if (t == 0) s_next = INDEX_TPB;
+    __syncthreads();
+
+    Parser ps;
     ps.init_parked();
-    uint32_t kleft = 0, ro = 0, tag = 0;   // blocks still to finish; first record of the region; (block & 31) << 9
+    uint32_t g = 0, cnt = 0, k = 0, o = 0, o_blk = 0, o_end = 0, written = 0, tag = 0;
     uint2* bi = nullptr;
     int cur = 0;
-    bool iframe = false;
-    if (g < seg_hi) {
-        const SegCtx c = seg_ctx(payload, streams, seg_stream, g);
-        const StreamDesc* sd = streams + c.sid;
-        const uint32_t nb = sd->nb, first = seg_first[g];
-        kleft = seg_blocks(seg_cnt, g, first, nb);
-        // A stream that ends early leaves the remaining blocks empty (zero coefficients).
-        if (c.seg + 1u == sd->nseg)
-            for (uint32_t b = min(first, nb) + kleft; b < nb; b++) blk_info[sd->block_base + b] = make_uint2(BLK_NO_SEG, 0);
-        if (kleft) {
-            const uint8_t* g0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(c.base + (size_t)c.seg * SEG_BYTES) & ~(uintptr_t)15);
-#pragma unroll 1
-            for (uint32_t u = 0; u < EMIT_UNITS; u++)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + u * 16u), "l"(g0 + u * 16u) : "memory");
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            ps.start_smem(c.base, seg_entry[g] + c.bias, c.seg_start + SEG_BITS, c.ftotal, g0, s0, EMIT_GUARD);
+    bool pframe = false;
+    uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // the last (o & 7) entries, newest in q[7]: stored one full 32-byte
+                                               // sector at a time (a partial-sector store makes L2 fetch the rest)
+    // Take segments from the CTA's counter until one holds blocks (cnt != 0) or none is left (cnt == 0).
+    auto grab = [&](uint32_t slot) {
+        for (;; slot = atomicAdd(&s_next, 1u)) {
+            k = 0; cnt = 0;
+            if (slot >= k_hi) { ps.park(); return; }
+            g = g0 + slot;
+            const SegCtx c = seg_ctx(payload, streams, seg_stream, g);
+            const StreamDesc* sd = streams + c.sid;
+            const uint32_t nb = sd->nb, first = seg_first[g];
+            cnt = first >= nb ? 0u : min(seg_cnt[g], nb - first);   // trailing pad bits can look like blocks
+            // A stream that ends early leaves the remaining blocks empty (zero coefficients).
+            if (c.seg + 1u == sd->nseg)
+                for (uint32_t b = first + cnt; b < nb; b++) blk_info[sd->block_base + b] = make_uint2(BLK_NO_SEG, 0);
+            if (cnt == 0) { seg_dc[g] = 0u; continue; }
+            ps.start(c.base, seg_entry[g] + c.bias, c.seg_start + SEG_BITS, c.ftotal);
             bi = blk_info + sd->block_base + first;
-            ro = (g - seg0) * REC_STRIDE;
-            tag = (first & 31u) << 9;
-            iframe = sd->ptype == 0;
+            tag = (first & 31u) << 6;                    // (index of the block being parsed & 31) << 6
+            o = o_blk = (g - sym_seg0) * SYM_STRIDE;     // chunk-relative entry index
+            o_end = o + SYM_STRIDE;
+            cur = 0;
+            pframe = sd->ptype != 0;
+            return;
         }
-    }
-    uint32_t o = 0, o_blk = 0, written = 0;      // o: records so far (warp-uniform); o_blk: the current block's DC record
-    int level = 0;
-    while (__any_sync(FULL_MASK, kleft != 0u)) {
-        uint32_t q[8];
-        const bool wr = kleft != 0u;
+    };
+    grab((uint32_t)t);
+    // (four steps per look at the loop condition: a lane that is done is parked, extra steps change nothing)
+    auto one_step = [&]() {
+        Parser::Sym y;
+        const bool end = ps.step<true, FOLD>(y);
+        if (y.dc) { cur = pframe ? y.e : cur + y.e; o_blk = o; }
+        if (y.coded && y.at < (64u << 24)) {             // (a parked lane never sees a coded symbol)
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            ParserT<FeedSmem>::Sym y;
-            const bool end = ps.step<true, FOLD>(y);
-            if (y.dc) { cur += y.e; level = iframe ? cur : y.e; o_blk = o + j; }   // lossless_decode.c:94 (I) / :91 (P)
-            const uint32_t lo = y.dc ? REC_DC : (y.coded ? (y.at >> 24) : REC_NONE);
-            q[j] = lo | tag | ((uint32_t)y.e << 16);
-            if (end && kleft) {
-                *bi++ = make_uint2(ro + o_blk, ((uint32_t)level & 0xFFFFu) | ((o + j + 1u - o_blk) << 16));
-                tag = (tag + (1u << 9)) & (31u << 9);
-                kleft--;
-                written = o + j + 1u;
+            for (int i = 0; i < 7; i++) q[i] = q[i + 1];
+            q[7] = (y.at >> 24) | tag | ((uint32_t)y.e << 16);
+            o++;
+            if ((o & 7u) == 0u && o <= o_end) st_global_v8(sym + o - 8, q);   // never overflows on conforming streams
+        }
+        if (end && k < cnt) {
+            bi[k] = make_uint2(min(o_blk, o_end - 1u), ((uint32_t)cur & 0xFFFFu) | ((min(o, o_end) - min(o_blk, o_end)) << 16));
+            tag = (tag + 64u) & 0x7C0u;
+            if (++k == cnt) {                            // segment done
+                seg_dc[g] = pframe ? 0u : ((uint32_t)cur & 0xFFFFu);
+                if ((o & 7u) && o < o_end) {             // flush the partial group (entries beyond o are never read)
+                    const uint32_t r = o & 7u;
+                    uint32_t v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {        // v[i] = q[8 - r + i] for i < r
+                        uint32_t x = 0;
+#pragma unroll
+                        for (int j = 1; j < 8; j++) if ((uint32_t)j == r && 8 - j + i < 8) x = q[8 - j + i];
+                        v[i] = x;
+                    }
+                    st_global_v8(sym + (o & ~7u), v);
+                }
+                written += min(o, o_end) - (o_end - SYM_STRIDE);
+                grab(atomicAdd(&s_next, 1u));
             }
         }
-        if (wr) st_global_v8(rec + ro + o, q);
-        o += 8u;
-        if (kleft == 0u) ps.park();      // done (at most 7 steps past its last block: inside the staged bytes)
-        if (o == REC_STRIDE) {           // non-conforming input: the region is full, the rest of the segment is dropped
-            for (; kleft; kleft--) *bi++ = make_uint2(ro + REC_STRIDE - 1u, 0u);
-            break;
-        }
+    };
+    while (__any_sync(FULL_MASK, cnt != 0u)) {
+        one_step();
+        one_step();
+        one_step();
+        one_step();
     }
-    {   // statistics: records written by this launch (one atomic per warp)
+    {   // statistics: list entries written by this launch (one atomic per warp)
 #pragma unroll
         for (int d = 16; d; d >>= 1) written += __shfl_xor_sync(FULL_MASK, written, d);
-        if ((threadIdx.x & 31) == 0 && written) atomicAdd(n_entries, (unsigned long long)written);
+        if ((t & 31) == 0 && written) atomicAdd(n_entries, (unsigned long long)written);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// DC predictors: one warp per stream.  A segment's DC total is the running sum its last block's index entry carries
-// (I frames; P-frame DC symbols are deltas against the previous frame: no predictor); the exclusive prefix sum mod
-// 2^16 of the totals is the value of `cur` (lossless_decode.c:73,94) entering each segment -> seg_dc.
+// DC predictors: one warp per stream turns seg_dc (the segments' DC totals) into the exclusive prefix
+// sum mod 2^16 = the value of `cur` (lossless_decode.c:73,94) entering each segment.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-k_entropy_dcscan(const StreamDesc* __restrict__ streams, uint32_t n_streams, const uint32_t* __restrict__ seg_cnt,
-                 const uint32_t* __restrict__ seg_first, const uint2* __restrict__ blk_info, uint32_t* __restrict__ seg_dc) {
+k_entropy_dcscan(const StreamDesc* __restrict__ streams, uint32_t n_streams, uint32_t* __restrict__ seg_dc) {
     const uint32_t s = blockIdx.x * 4u + (threadIdx.x >> 5);
     if (s >= n_streams) return;
     const StreamDesc sd = streams[s];
     const int lane = threadIdx.x & 31;
+    uint32_t* v = seg_dc + sd.seg_base;
     uint32_t carry = 0;
     for (uint32_t i0 = 0; i0 < sd.nseg; i0 += 32) {
-        const uint32_t i = i0 + lane, g = sd.seg_base + i;
-        uint32_t x = 0;
-        if (i < sd.nseg && sd.ptype == 0) {
-            const uint32_t first = seg_first[g], cnt = seg_blocks(seg_cnt, g, first, sd.nb);
-            if (cnt) x = blk_info[sd.block_base + first + cnt - 1u].y & 0xFFFFu;
-        }
+        const uint32_t i = i0 + lane;
+        const uint32_t x = i < sd.nseg ? v[i] : 0u;
         uint32_t inc = x;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t a = __shfl_up_sync(FULL_MASK, inc, d);
             if (lane >= d) inc += a;
         }
-        if (i < sd.nseg) seg_dc[g] = (carry + inc - x) & 0xFFFFu;
+        if (i < sd.nseg) v[i] = (carry + inc - x) & 0xFFFFu;
         carry += __shfl_sync(FULL_MASK, inc, 31);
     }
 }
@@ -567,20 +571,21 @@ cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s) {
                                                       j.d_stream_blocks + j.stream_lo, j.d_fixups);
     return cudaGetLastError();
 }
-cudaError_t launch_entropy_emit(const EntropyJob& j, cudaStream_t s) {
+cudaError_t launch_entropy_index(const EntropyJob& j, cudaStream_t s) {
     if (j.seg_hi <= j.seg_lo) return cudaSuccess;
     const uint32_t n = j.seg_hi - j.seg_lo;
-    const unsigned grid = (n + EMIT_TPB - 1) / EMIT_TPB;
-    if (j.fold_end || getenv("MJ_EMIT_FOLD"))
-        k_entropy_emit<true><<<grid, EMIT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry,
-                                                       j.d_seg_cnt, j.d_seg_first, j.d_blk_info, j.d_rec, j.seg0, j.d_fixups + 1);
+    const unsigned grid = (n + INDEX_SLOTS - 1) / INDEX_SLOTS;
+    if (j.fold_end)
+        k_entropy_index<true><<<grid, INDEX_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry,
+                                                         j.d_seg_cnt, j.d_seg_first, j.d_seg_dc, j.d_blk_info, j.d_sym, j.sym_seg0,
+                                                         j.d_fixups + 1);
     else
-        k_entropy_emit<false><<<grid, EMIT_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry,
-                                                        j.d_seg_cnt, j.d_seg_first, j.d_blk_info, j.d_rec, j.seg0, j.d_fixups + 1);
+        k_entropy_index<false><<<grid, INDEX_TPB, 0, s>>>(j.d_payload, j.d_streams, j.d_seg_stream, j.seg_lo, j.seg_hi, j.d_seg_entry,
+                                                          j.d_seg_cnt, j.d_seg_first, j.d_seg_dc, j.d_blk_info, j.d_sym, j.sym_seg0,
+                                                          j.d_fixups + 1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k_entropy_dcscan<<<(j.n_streams + 3) / 4, 128, 0, s>>>(j.d_streams + j.stream_lo, j.n_streams, j.d_seg_cnt, j.d_seg_first,
-                                                          j.d_blk_info, j.d_seg_dc);
+    k_entropy_dcscan<<<(j.n_streams + 3) / 4, 128, 0, s>>>(j.d_streams + j.stream_lo, j.n_streams, j.d_seg_dc);
     return cudaGetLastError();
 }
 

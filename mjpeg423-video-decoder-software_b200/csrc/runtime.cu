@@ -149,15 +149,6 @@ void make_chunks(const Plan& plan, uint32_t K, std::vector<Chunk>& chunks, std::
     }
 }
 
-size_t chunk_scratch_bytes(size_t segs, size_t blocks) {
-    return ((blocks * 8 + 255) & ~(size_t)255) + segs * (size_t)REC_STRIDE * 4 + 256;
-}
-void carve_chunk_scratch(EntropyJob& j, void* base, size_t blocks, size_t first_block) {
-    uint8_t* w = static_cast<uint8_t*>(base);
-    j.d_blk_info = reinterpret_cast<uint2*>(w) - first_block;     // StreamDesc.block_base is plan-relative
-    j.d_rec = reinterpret_cast<uint32_t*>(w + ((blocks * 8 + 255) & ~(size_t)255));
-}
-
 }  // namespace mj
 
 using namespace mj;
@@ -347,10 +338,11 @@ int decode_mode(const mjpeg423_b200_ctx* c, const Plan& plan) {
     return c->staged;
 }
 
-// Per-chunk scratch: block index (8 bytes per block) + record lists (REC_STRIDE records per segment) and, in the
-// staged modes, coefficient planes.
+// Per-chunk scratch: block index (8 bytes per block) + symbol lists (SYM_STRIDE entries per segment) and,
+// in the staged modes, coefficient planes.
 size_t chunk_index_bytes(const Plan& plan, uint32_t f0, uint32_t f1) {
-    return chunk_scratch_bytes(plan.f_seg0[f1] - plan.f_seg0[f0], (size_t)(f1 - f0) * 3 * plan.nb);
+    const size_t blocks = (size_t)(f1 - f0) * 3 * plan.nb, segs = plan.f_seg0[f1] - plan.f_seg0[f0];
+    return blocks * 8 + 32 + segs * (size_t)SYM_STRIDE * 4 + 256;
 }
 int reserve_chunk_buffers(mjpeg423_b200_ctx* c, const Plan& plan, const std::vector<Chunk>& chunks, int nbuf) {
     size_t idx_bytes = 0, frames = 0;
@@ -385,8 +377,13 @@ EntropyJob make_job(const Plan& plan, const Tables& t, const uint8_t* d_payload_
     j.d_seg_entry = t.seg_entry; j.d_seg_exit = t.seg_exit; j.d_seg_cnt = t.seg_cnt; j.d_seg_first = t.seg_first;
     j.d_seg_dc = t.seg_dc;
     j.d_stream_blocks = t.stream_blocks; j.d_fixups = t.fixups;
-    j.seg0 = plan.f_seg0[f0];
-    carve_chunk_scratch(j, d_blkidx, (size_t)(f1 - f0) * 3 * plan.nb, (size_t)f0 * 3 * plan.nb);
+    // StreamDesc.block_base is plan-relative: shift the chunk buffers back by the chunk's first block
+    // ... and StreamDesc.seg_base too: same for the symbol lists
+    const size_t blocks = (size_t)(f1 - f0) * 3 * plan.nb, first_block = (size_t)f0 * 3 * plan.nb;
+    uint32_t* w = static_cast<uint32_t*>(d_blkidx);
+    j.d_blk_info = reinterpret_cast<uint2*>(w) - first_block;
+    j.d_sym = w + ((2 * blocks + 7) & ~(size_t)7);   // 32-byte aligned; entries are relative to the chunk's first segment
+    j.sym_seg0 = plan.f_seg0[f0];
     return j;
 }
 
@@ -406,9 +403,9 @@ int enqueue_chunk(mjpeg423_b200_ctx* c, const Plan& plan, const Tables& t, const
     if (prof) CU(cudaEventRecord(prof[1], s));
     if (!synced) CU(launch_entropy_chain(j, s));
     if (prof) CU(cudaEventRecord(prof[2], s));
-    CU(launch_entropy_emit(j, s));
+    CU(launch_entropy_index(j, s));
     if (prof) CU(cudaEventRecord(prof[3], s));
-    c->stats.kernel_launches += synced ? 2 : 4;       // emit + DC scan (+ sync + chain)
+    c->stats.kernel_launches += synced ? 2 : 4;
     if (mode == 0) {
         const uint32_t* d_gops = nullptr;
         if (plan.n_pframes) {                    // GOP-walking variant; its scratch belongs to this chunk buffer
@@ -495,13 +492,13 @@ extern "C" int mjpeg423_b200_upload(mjpeg423_b200_ctx* c, const uint8_t* mpg, si
     rc = build_plan(idx, first, n, c->plan);
     if (rc) return rc;
     if (n == 0) { c->have_plan = true; return MJPEG423_OK; }
-    rc = c->payload.reserve(c->plan.payload_len + PAYLOAD_PAD);       // + look-ahead pad
+    rc = c->payload.reserve(c->plan.payload_len + 64);       // + look-ahead pad
     if (rc) return rc;
     Tables t;
     rc = upload_tables(c, c->plan, t, c->s_compute);
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->payload.p, mpg + c->plan.payload_off, c->plan.payload_len, cudaMemcpyHostToDevice, c->s_compute));
-    CU(cudaMemsetAsync(c->payload.as<uint8_t>() + c->plan.payload_len, 0, PAYLOAD_PAD, c->s_compute));
+    CU(cudaMemsetAsync(c->payload.as<uint8_t>() + c->plan.payload_len, 0, 64, c->s_compute));
     CU(cudaStreamSynchronize(c->s_compute));
     c->have_plan = true;
     return MJPEG423_OK;
@@ -515,11 +512,10 @@ extern "C" int mjpeg423_b200_decode_resident(mjpeg423_b200_ctx* c, void* d_out) 
     if (plan.n == 0) return MJPEG423_OK;
     if (!d_out) return MJPEG423_E_ARG;
     Tables t = tables_of(c, plan);
-    // chunk size: bounded scratch (records + block index, + 128 B/block of coefficients and 64 of samples in the
-    // staged modes)
-    const size_t scratch_frame = chunk_scratch_bytes(plan.f_seg0.back() / plan.n + 1, (size_t)3 * plan.nb) +
-                                 (size_t)3 * plan.nb * (decode_mode(c, plan) == 2 ? 192 : decode_mode(c, plan) ? 128 : 0);
-    const uint32_t K = c->chunk_frames ? std::min(c->chunk_frames, plan.n) : auto_chunk(plan, (uint64_t)4 << 30, scratch_frame);
+    // chunk size: bounded scratch (block index 6 B/block, + 128 B/block of coefficients in the staged modes)
+    const size_t scratch_frame = (size_t)3 * plan.nb * (decode_mode(c, plan) ? 136 : 8) +
+                                 (size_t)(plan.f_seg0.back() / plan.n + 1) * SYM_STRIDE * 4;
+    const uint32_t K = c->chunk_frames ? std::min(c->chunk_frames, plan.n) : auto_chunk(plan, (uint64_t)3 << 30, scratch_frame);
     int rc = prepare_chunks(c, plan, K, c->s_compute);
     if (rc) return rc;
     const int nbuf = (c->chunks.size() > 1 && !c->profile) ? 2 : 1;
@@ -599,7 +595,7 @@ extern "C" int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* c, int16_t* d_c
     CU(cudaEventRecord(e[1], s));
     CU(launch_entropy_chain(j, s));
     CU(cudaEventRecord(e[2], s));
-    CU(launch_entropy_emit(j, s));
+    CU(launch_entropy_index(j, s));
     CU(cudaEventRecord(e[3], s));
     const uint32_t* ids = c->ids.as<uint32_t>() + ch.ids_off;
     for (size_t l = 0; l + 1 < ch.level_off.size(); l++) {
@@ -679,7 +675,7 @@ extern "C" int mjpeg423_b200_decode_frames(mjpeg423_b200_ctx* c, const uint8_t* 
     for (const Chunk& ch : c->chunks)
         max_in = std::max<size_t>(max_in, plan.frames[ch.f1 - 1].off + plan.frames[ch.f1 - 1].size - plan.frames[ch.f0].off);
     for (int i = 0; i < 2; i++) {
-        if ((rc = c->in_ring[i].reserve(max_in + PAYLOAD_PAD))) return rc;
+        if ((rc = c->in_ring[i].reserve(max_in + 64))) return rc;
         if (!out_on_device && (rc = c->out_ring[i].reserve((size_t)maxf * frame_bytes))) return rc;
     }
     cudaEvent_t ev_start = c->ev[0], ev_stop = c->ev[1];
@@ -699,7 +695,7 @@ extern "C" int mjpeg423_b200_decode_frames(mjpeg423_b200_ctx* c, const uint8_t* 
         // upload: the slot is free once the chunk that used it two iterations ago has been decoded
         if (k >= 2) CU(cudaStreamWaitEvent(c->s_in, ev_comp[b], 0));
         CU(cudaMemcpyAsync(c->in_ring[b].p, mpg + in_off, in_len, cudaMemcpyHostToDevice, c->s_in));
-        CU(cudaMemsetAsync(c->in_ring[b].as<uint8_t>() + in_len, 0, PAYLOAD_PAD, c->s_in));
+        CU(cudaMemsetAsync(c->in_ring[b].as<uint8_t>() + in_len, 0, 64, c->s_in));
         CU(cudaEventRecord(ev_in[b], c->s_in));
         // decode
         CU(cudaStreamWaitEvent(c->s_compute, ev_in[b], 0));

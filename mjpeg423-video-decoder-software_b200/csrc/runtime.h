@@ -27,25 +27,19 @@ struct EntropyJob {
     uint32_t* d_seg_dc = nullptr;                // plan-wide: DC total, then DC predictor, of every segment
     uint32_t* d_stream_blocks = nullptr;         // plan-wide, per stream
     unsigned long long* d_fixups = nullptr;
-    // chunk scratch (see common.cuh): the block index is addressed by StreamDesc.block_base + b, segment g's records
-    // start at (g - seg0) * REC_STRIDE
-    uint2* d_blk_info = nullptr;
-    uint32_t* d_rec = nullptr;
-    uint32_t seg0 = 0;
+    uint2* d_blk_info = nullptr;                 // block index, addressed by StreamDesc.block_base + b
+    uint32_t* d_sym = nullptr;                   // symbol lists: segment g's region starts at (g - sym_seg0) * SYM_STRIDE
+    uint32_t sym_seg0 = 0;
 };
 
 cudaError_t launch_seg_stream(const StreamDesc* d_streams, uint32_t n_streams, uint32_t* d_seg_stream, cudaStream_t s);
 cudaError_t launch_entropy_sync(const EntropyJob& j, cudaStream_t s);
 cudaError_t launch_entropy_chain(const EntropyJob& j, cudaStream_t s);
-cudaError_t launch_entropy_emit(const EntropyJob& j, cudaStream_t s);    // + DC scan
+cudaError_t launch_entropy_index(const EntropyJob& j, cudaStream_t s);
 cudaError_t launch_decode_coef(const EntropyJob& j, const uint32_t* d_stream_ids, uint32_t n_ids, uint32_t nb,
                                const int16_t* d_quant, int16_t* d_coef, cudaStream_t s);
 // d_gop_first == nullptr: intra-only range.  Otherwise d_gop_first[0 .. n_gops] = chunk-relative first frames of the
 // range's GOPs (+ its end) and d_state = FUSED_STATE_BYTES of scratch that no other launch in flight uses.
-// Bytes of chunk scratch for `segs` segments and `blocks` blocks (EntropyJob::d_blk_info / d_rec); carve() points the job
-// at it (first_block = the plan-relative index of the chunk's first block).
-size_t chunk_scratch_bytes(size_t segs, size_t blocks);
-void carve_chunk_scratch(EntropyJob& j, void* base, size_t blocks, size_t first_block);
 constexpr int FUSED_MAX_CTAS = 192;                                     // persistent grid: one CTA per SM, at most this many
 constexpr size_t FUSED_STATE_BYTES = (size_t)FUSED_MAX_CTAS * 18 * 3 * 8 * 32 * 16;   // 12 KB per warp
 cudaError_t launch_decode_fused(const EntropyJob& j, const int16_t* d_quant, void* d_out, uint32_t n_frames,
