@@ -47,8 +47,10 @@ typedef struct { uint8_t blue, green, red, alpha; } rgb_pixel_t; /* :56-61, BMP 
 /* ---- 1. reference library seam: LIB/decoder/mjpeg423_decoder.h:14-17 ------------------------------ */
 /* P is the reference's `bool` (int).  DCACq is in/out: for P != 0 decoded deltas are ADDED to it
  * (LIB/decoder/lossless_decode.c:90-92,121-123).  The bitstream must be readable 4 bytes past its last
- * symbol; because the reference signature carries no length, the shim reads at most
- * mjpeg423_b200_get_read_limit() bytes (default: num_blocks*152 + 8, the longest conforming stream). */
+ * symbol.  The reference signature carries no length: the shim first walks the symbol headers of
+ * num_blocks blocks on the host to find where the stream ends (it reads no byte the reference decoder would not read)
+ * and uploads exactly that; mjpeg423_b200_set_read_limit() bounds the walk for non-conforming input (default:
+ * num_blocks*184 + 8 bytes, the longest stream the reference decoder accepts). */
 void lossless_decode(int num_blocks, void* bitstream, dct_block_t* DCACq, dct_block_t quant, int P);
 void idct(dct_block_t DCAC, color_block_t block);
 void ycbcr_to_rgb(int h, int w, uint32_t w_size, pcolor_block_t Y, pcolor_block_t Cb, pcolor_block_t Cr,
@@ -84,6 +86,11 @@ void idct_accel_calculate_buffer_y(void* inputBuffer, uint32_t sizeOfInputBuffer
 void idct_accel_calculate_buffer_cb(void* inputBuffer, uint32_t sizeOfInputBuffer);
 void idct_accel_calculate_buffer_cr(void* inputBuffer, uint32_t sizeOfInputBuffer);
 void ycbcr_to_rgb_accel_get_results(void* outputBuffer, uint32_t sizeOfOutputBuffer);
+/* C0/idct_ycbcr_to_rgb_accel.h:19-20 (declared in the reference, no body there): colour conversion of
+ * hCb_size x wCb_size sample blocks (block-major planes; argument order Y, Cr, Cb as in the reference) into the
+ * raster outputBuffer with rows of w_size pixels; asynchronous like the calls above. */
+void ycbcr_to_rgb_accel_calculate_buffer(color_block_t* yBlock, color_block_t* crBlock, color_block_t* cbBlock,
+                                         rgb_pixel_t* outputBuffer, int hCb_size, int wCb_size, int w_size);
 void wait_for_ycbcr_to_rgb_finsh(void);   /* sic: reference spelling */
 void wait_for_idct_y_finsh(void);
 int  mjpeg423_b200_accel_set_geometry(uint32_t w_size, uint32_t h_size);
@@ -183,6 +190,37 @@ int   mjpeg423_b200_device_count(void);
  * is host memory.  Used by the bench for whole-batch bit-exactness checks. */
 int   mjpeg423_b200_hash_frames(mjpeg423_b200_ctx* ctx, const void* d_frames, uint64_t frame_bytes, uint32_t n,
                                 uint64_t* hashes);
+
+/* ---- 3b. container index and seek ---------------------------------------------------- */
+/* The I-frame index of a .mpg: one iframe_trailer_t {frame_index, frame_position = file offset of the frame's
+ * frame_size field} per I frame, in file order -- what the reference reads from the trailer at 20 + payload_size
+ * (LIB/decoder/mjpeg423_decoder.c:78-86, C1/main.c:77-113).  The entries are rebuilt from a bounds-checked walk over
+ * the frame headers and COMPARED with the file's trailer: *trailer_ok (may be NULL) is 1 when the trailer is present and
+ * says the same, 0 when it is missing, truncated or wrong (the index returned is valid either way).  out may be NULL to
+ * query *n_iframes; cap = entries out can hold. */
+int mjpeg423_b200_index(const uint8_t* mpg, size_t len, iframe_trailer_t* out, uint32_t cap, uint32_t* n_iframes,
+                        int* trailer_ok);
+/* Position in idx[] of the I frame a decode of `frame` must start from (direction <= 0: the last I frame at or before
+ * it) or of the first I frame at or after it (direction > 0); -1 if there is none. */
+int mjpeg423_b200_seek_iframe(const iframe_trailer_t* idx, uint32_t n, uint32_t frame, int direction);
+/* The player's jumps, C0/playback.c:157-227: fast-forward = the first I frame at least 108 frames ahead of `current`
+ * (-1 = nothing happens: fewer than 120 frames left); rewind = the last I frame at least 108 frames back (entry 0 when
+ * `current` is less than 120 frames from the start).  Both return a position in idx[]. */
+int mjpeg423_b200_fast_forward(const iframe_trailer_t* idx, uint32_t n, uint32_t num_frames, uint32_t current);
+int mjpeg423_b200_rewind(const iframe_trailer_t* idx, uint32_t n, uint32_t current);
+
+/* ---- 3c. frame-range sharding over the GPUs of one box (SURVEY.md 8 row e) ------------------------------------ */
+/* Frames [first, first + n) of the logical stream formed by n_shards .mpg files in order (one file is the common case;
+ * long streams come as several files because the container's offsets are 32-bit, LIB/encoder/mjpeg423_encoder.c:67,
+ * 209,222-225; all files must share one geometry and start on an I frame) are decoded on n_dev devices: the range is cut
+ * into n_dev contiguous pieces on I frames, one host thread per device runs mjpeg423_b200_decode_frames on its piece
+ * and writes its slice of `out` (host memory, n x frame_bytes; pinned memory gives full PCIe speed).  No data moves
+ * between GPUs.  devices = NULL means 0 .. n_dev-1; a device may be listed more than once (one context per entry).
+ * cuts (may be NULL) receives the n_dev + 1 piece boundaries.  The tables set with mjpeg423_b200_set_quant do not
+ * apply: the per-device contexts are private to this call and use Yquant / Cquant. */
+typedef struct { const uint8_t* mpg; size_t len; } mjpeg423_b200_shard;
+int mjpeg423_b200_decode_frames_multi(const int* devices, int n_dev, const mjpeg423_b200_shard* shards, uint32_t n_shards,
+                                      uint64_t first, uint64_t n, void* out, uint64_t* cuts);
 
 /* ---- 4. encoder: LIB/encoder/mjpeg423_encoder.h ---------------------------------- */
 /* The frame loop of mjpeg423_encode(), LIB/encoder/mjpeg423_encoder.c:97-225, on in-memory frames: n frames of

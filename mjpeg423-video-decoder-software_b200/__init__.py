@@ -13,6 +13,6 @@ There is no CPU fallback: every decode entry raises if the CUDA library is missi
 """
 from . import build, synth  # noqa: F401
 from .api import (  # noqa: F401
-    CQUANT, YQUANT, ZIGZAG, Decoder, Display, MpgInfo, idct, lossless_decode, load_library, mjpeg423_decode, play, probe,
+    CQUANT, YQUANT, ZIGZAG, Decoder, Display, IFrameIndex, MpgInfo, decode_frames_multi, idct, lossless_decode, load_library, mjpeg423_decode, play, probe,
     write_bmp, ycbcr_to_rgb,
 )

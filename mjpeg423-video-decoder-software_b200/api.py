@@ -42,7 +42,9 @@ EXPORTS = [
     "mjpeg423_b200_ycbcr_to_rgb_frame", "mjpeg423_b200_lossless_decode",
     "init_idct_ycbcr_to_rgb_accel", "idct_accel_calculate_buffer_y", "idct_accel_calculate_buffer_cb",
     "idct_accel_calculate_buffer_cr", "ycbcr_to_rgb_accel_get_results", "wait_for_ycbcr_to_rgb_finsh",
-    "wait_for_idct_y_finsh", "mjpeg423_b200_accel_set_geometry",
+    "wait_for_idct_y_finsh", "mjpeg423_b200_accel_set_geometry", "ycbcr_to_rgb_accel_calculate_buffer",
+    "mjpeg423_b200_index", "mjpeg423_b200_seek_iframe", "mjpeg423_b200_fast_forward", "mjpeg423_b200_rewind",
+    "mjpeg423_b200_decode_frames_multi",
     "mjpeg423_b200_create", "mjpeg423_b200_destroy", "mjpeg423_b200_set_option", "mjpeg423_b200_last_error",
     "mjpeg423_b200_probe", "mjpeg423_b200_set_quant", "mjpeg423_b200_decode_frames", "mjpeg423_b200_upload",
     "mjpeg423_b200_decode_resident", "mjpeg423_b200_get_stats", "mjpeg423_b200_resident_entropy",
@@ -121,6 +123,12 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "wait_for_ycbcr_to_rgb_finsh": (None, []),
         "wait_for_idct_y_finsh": (None, []),
         "mjpeg423_b200_accel_set_geometry": (i32, [u32, u32]),
+        "ycbcr_to_rgb_accel_calculate_buffer": (None, [p, p, p, p, i32, i32, i32]),
+        "mjpeg423_b200_index": (i32, [p, sz, p, u32, C.POINTER(u32), C.POINTER(i32)]),
+        "mjpeg423_b200_seek_iframe": (i32, [p, u32, u32, i32]),
+        "mjpeg423_b200_fast_forward": (i32, [p, u32, u32, u32]),
+        "mjpeg423_b200_rewind": (i32, [p, u32, u32]),
+        "mjpeg423_b200_decode_frames_multi": (i32, [p, i32, p, u32, u64, u64, p, p]),
         "mjpeg423_b200_create": (i32, [C.POINTER(p), i32]),
         "mjpeg423_b200_destroy": (None, [p]),
         "mjpeg423_b200_set_option": (i32, [p, i32, C.c_int64]),
@@ -262,6 +270,60 @@ def probe(mpg) -> MpgInfo:
 
 
 # ---- batched frame-range decoder --------------------------------------------------------------------------
+class _Shard(C.Structure):
+    _fields_ = [("mpg", C.c_void_p), ("len", C.c_size_t)]
+
+
+class IFrameIndex:
+    """The I-frame index of a .mpg: `entries` is an (n, 2) uint32 array of {frame_index,
+    frame_position}, the layout of the reference's iframe_trailer_t (LIB/common/mjpeg423_types.h:22-25);
+    trailer_ok says whether the file's own trailer agrees with the header walk.  Host only: no GPU needed."""
+
+    def __init__(self, mpg):
+        lib = load_library()
+        a = _bytes_arr(mpg)
+        n, ok = C.c_uint32(0), C.c_int(0)
+        _check(lib, lib.mjpeg423_b200_index(a.ctypes.data, a.size, None, 0, C.byref(n), C.byref(ok)), "index")
+        self.entries = np.zeros((n.value, 2), dtype=np.uint32)
+        _check(lib, lib.mjpeg423_b200_index(a.ctypes.data, a.size, self.entries.ctypes.data, n.value, C.byref(n), C.byref(ok)), "index")
+        self.trailer_ok = bool(ok.value)
+        self._lib = lib
+
+    def __len__(self):
+        return len(self.entries)
+
+    def seek(self, frame: int, direction: int = 0) -> int:
+        return self._lib.mjpeg423_b200_seek_iframe(self.entries.ctypes.data, len(self.entries), frame, direction)
+
+    def fast_forward(self, num_frames: int, current: int) -> int:
+        return self._lib.mjpeg423_b200_fast_forward(self.entries.ctypes.data, len(self.entries), num_frames, current)
+
+    def rewind(self, current: int) -> int:
+        return self._lib.mjpeg423_b200_rewind(self.entries.ctypes.data, len(self.entries), current)
+
+
+def decode_frames_multi(files, devices, first: int = 0, n: int | None = None, out: np.ndarray | None = None):
+    """Frame-range sharding over the GPUs of one box: `files` is one .mpg or a list of them forming one
+    logical stream, `devices` a list of device ordinals (a device may appear twice).  Returns (frames, cuts)."""
+    lib = load_library()
+    _require_gpu(lib)
+    if isinstance(files, (bytes, bytearray, np.ndarray)):
+        files = [files]
+    arrs = [_bytes_arr(f) for f in files]
+    infos = [probe(a) for a in arrs]
+    total = sum(i.num_frames for i in infos)
+    if n is None:
+        n = total - first
+    shards = (_Shard * len(arrs))(*[_Shard(a.ctypes.data, a.size) for a in arrs])
+    devs = (C.c_int * len(devices))(*devices)
+    cuts = np.zeros(len(devices) + 1, dtype=np.uint64)
+    if out is None:
+        out = np.empty((n, infos[0].h_size, infos[0].w_size, 4), dtype=np.uint8)
+    rc = lib.mjpeg423_b200_decode_frames_multi(devs, len(devices), shards, len(arrs), first, n, out.ctypes.data, cuts.ctypes.data)
+    _check(lib, rc, "decode_frames_multi")
+    return out, cuts
+
+
 class PinnedBuffer:
     """Pinned host memory from the library, viewed as a numpy array."""
 

@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_CUDA = os.path.join(PKG_DIR, "libmjpeg423_b200.so")
 LIB_SYNTH = os.path.join(PKG_DIR, "libmjpeg423_synth.so")
 
-CUDA_SOURCES = ["entropy.cu", "decode.cu", "idct_colour.cu", "encode.cu", "display.cu", "runtime.cu", "cabi.cu"]
+CUDA_SOURCES = ["entropy.cu", "decode.cu", "idct_colour.cu", "encode.cu", "display.cu", "runtime.cu", "multi.cu", "cabi.cu"]
 CUDA_HEADERS = ["common.cuh", "runtime.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

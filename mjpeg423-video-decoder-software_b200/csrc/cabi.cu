@@ -173,11 +173,46 @@ int mjpeg423_b200_lossless_decode(int num_blocks, const void* bitstream, size_t 
     return single_stream_decode(c, num_blocks, bitstream, bitstream_len, DCACq, quant, P);
 }
 
+// The reference signature carries no length.  So that the shim touches no byte the reference would not have touched
+// itself, the extent of the stream is found first: a walk over the SYMBOL HEADERS of num_blocks blocks with the control
+// flow of LIB/decoder/lossless_decode.c:84-133 (4-bit size / run + size nibbles; no amplitude is decoded, no
+// coefficient produced -- the decode itself runs on the GPU).  Stops at `limit` bytes.
+static size_t stream_extent(int num_blocks, const uint8_t* p, size_t limit) {
+    uint64_t bit = 0;
+    auto nib = [&](uint64_t b) -> unsigned {             // the 4 bits at bit position b (reads p[i + 1] only when they reach into it)
+        const size_t i = (size_t)(b >> 3);
+        const unsigned sh = (unsigned)(b & 7);
+        const unsigned v = ((unsigned)p[i] << 8) | (sh > 4 ? p[i + 1] : 0u);
+        return (v >> (12 - sh)) & 15u;
+    };
+    for (int blk = 0; blk < num_blocks; blk++) {
+        if ((bit >> 3) + 2 > limit) return limit;
+        bit += 4 + nib(bit);                             // input_DC, :210-224
+        uint8_t index = 1;                               // :100
+        for (;;) {
+            if ((bit >> 3) + 3 > limit) return limit;
+            const unsigned run = nib(bit), size = nib(bit + 4);   // input_AC, :227-246
+            bit += 8 + size;
+            if (size == 0) {
+                if (run == 15) index = (uint8_t)(index + 16);     // ZRL, :106-109
+                else break;                                       // END, :110-113
+            } else {
+                index = (uint8_t)(index + run);
+                if (index >= 63) break;                           // :130
+                index++;
+            }
+        }
+    }
+    const size_t bytes = (size_t)((bit + 7) >> 3);
+    return bytes < limit ? bytes : limit;
+}
+
 void lossless_decode(int num_blocks, void* bitstream, dct_block_t* DCACq, dct_block_t quant, int P) {
-    // The reference signature has no length: read up to the longest conforming stream
-    // (15 + 63*19 = 1212 bits = 152 bytes per block) or the configured limit.
-    size_t len = (size_t)(num_blocks > 0 ? num_blocks : 0) * 152 + 8;
-    if (g_read_limit && g_read_limit < len) len = g_read_limit;
+    // Upper bound of the walk: the longest stream the reference decoder accepts (19 + 63 * 23 = 1468 bits = 184 bytes per
+    // block) or the configured limit.
+    size_t limit = (size_t)(num_blocks > 0 ? num_blocks : 0) * 184 + 8;
+    if (g_read_limit && g_read_limit < limit) limit = g_read_limit;
+    const size_t len = bitstream ? stream_extent(num_blocks, static_cast<const uint8_t*>(bitstream), limit) : 0;
     if (mjpeg423_b200_lossless_decode(num_blocks, bitstream, len, &DCACq[0][0][0], &quant[0][0], P) != MJPEG423_OK)
         die("lossless_decode");
 }
@@ -283,6 +318,29 @@ void ycbcr_to_rgb_accel_get_results(void* outputBuffer, uint32_t sizeOfOutputBuf
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(outputBuffer, g_accel.out.p, sizeOfOutputBuffer, cudaMemcpyDeviceToHost, c->s_compute);
     if (e != cudaSuccess) { cuda_fail(e, "accelerator launch"); die("ycbcr_to_rgb_accel_get_results"); }
+}
+// C0/idct_ycbcr_to_rgb_accel.h:19-20 (declared there without a body): colour conversion of hCb_size x wCb_size sample
+// blocks (block-major planes; note the reference's argument order Y, Cr, Cb) into the raster outputBuffer, whose rows
+// are w_size pixels long.  Enqueued like the other accelerator calls; wait_for_ycbcr_to_rgb_finsh() completes it.
+void ycbcr_to_rgb_accel_calculate_buffer(color_block_t* yBlock, color_block_t* crBlock, color_block_t* cbBlock,
+                                         rgb_pixel_t* outputBuffer, int hCb_size, int wCb_size, int w_size) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    mjpeg423_b200_ctx* c = shim_ctx();
+    if (!c || !g_accel.inited) { set_error("accelerator not initialised"); die("ycbcr_to_rgb_accel_calculate_buffer"); }
+    if (!yBlock || !crBlock || !cbBlock || !outputBuffer || hCb_size <= 0 || wCb_size <= 0 || w_size < wCb_size * 8) {
+        set_error("bad argument"); die("ycbcr_to_rgb_accel_calculate_buffer");
+    }
+    const size_t nb = (size_t)hCb_size * wCb_size;
+    const uint32_t W = (uint32_t)wCb_size * 8, H = (uint32_t)hCb_size * 8;
+    if (s_in.reserve(3 * nb * 64) || s_out.reserve(nb * 256)) die("ycbcr_to_rgb_accel_calculate_buffer");
+    cudaStream_t s = c->s_compute;
+    cudaError_t e = cudaMemcpyAsync(s_in.as<uint8_t>(), yBlock, nb * 64, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s_in.as<uint8_t>() + nb * 64, cbBlock, nb * 64, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s_in.as<uint8_t>() + 2 * nb * 64, crBlock, nb * 64, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = launch_colour(s_in.as<uint8_t>(), s_out.p, 1, W, H, s);
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(outputBuffer, (size_t)w_size * 4, s_out.p, (size_t)W * 4, (size_t)W * 4, H, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) { cuda_fail(e, "accelerator colour conversion"); die("ycbcr_to_rgb_accel_calculate_buffer"); }
 }
 void wait_for_ycbcr_to_rgb_finsh(void) {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -20,6 +20,8 @@
 //
 // Slots use the XOR swizzle of idct_colour.cu (16-byte chunk r of slot t at chunk r ^ (t & 7)), so both
 // the row reads of the IDCT and the cooperative copy-out are bank-conflict free.
+#include <mutex>
+
 #include "common.cuh"
 #include "runtime.h"
 
@@ -62,14 +64,15 @@ __device__ __forceinline__ uint32_t absolute_dc(uint2 info, const uint32_t* __re
 // ---- coefficient planes ------------------------------------------------------------------------------
 // grid = (ceil(nb / 128), number of streams in `stream_ids`).
 __global__ void __launch_bounds__(DEC_TPB)
-k_decode_coef(const StreamDesc* __restrict__ streams, const uint32_t* __restrict__ stream_ids,
+k_decode_coef(const StreamDesc* __restrict__ streams, const uint32_t* __restrict__ stream_ids, uint32_t groups,
               const uint2* __restrict__ blk_info, const uint32_t* __restrict__ sym, const uint32_t* __restrict__ seg_dc,
               const int16_t* __restrict__ quant, int16_t* coef) {
     __shared__ __align__(128) uint8_t slots[DEC_TPB * 128];
     __shared__ uint32_t s_zq[64];
     const int t = threadIdx.x;
-    const StreamDesc sd = streams[stream_ids[blockIdx.y]];
-    const uint32_t b0 = blockIdx.x * DEC_TPB;
+    const uint32_t id = blockIdx.x / groups, grp = blockIdx.x - id * groups;   // (gridDim.y is capped at 65535)
+    const StreamDesc sd = streams[stream_ids[id]];
+    const uint32_t b0 = grp * DEC_TPB;
     if (b0 >= sd.nb) return;
     const uint32_t nblk = min((uint32_t)DEC_TPB, sd.nb - b0);
     load_zq(s_zq, quant + sd.quant_id * 64, t);
@@ -525,8 +528,9 @@ k_decode_fused(const uint2* __restrict__ blk_info,
 cudaError_t launch_decode_coef(const EntropyJob& j, const uint32_t* d_stream_ids, uint32_t n_ids, uint32_t nb,
                                const int16_t* d_quant, int16_t* d_coef, cudaStream_t s) {
     if (n_ids == 0 || nb == 0) return cudaSuccess;
-    dim3 grid((nb + DEC_TPB - 1) / DEC_TPB, n_ids);
-    k_decode_coef<<<grid, DEC_TPB, 0, s>>>(j.d_streams, d_stream_ids, j.d_blk_info, j.d_sym, j.d_seg_dc + j.sym_seg0,
+    const uint32_t groups = (nb + DEC_TPB - 1) / DEC_TPB;
+    if ((uint64_t)groups * n_ids > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+    k_decode_coef<<<groups * n_ids, DEC_TPB, 0, s>>>(j.d_streams, d_stream_ids, groups, j.d_blk_info, j.d_sym, j.d_seg_dc + j.sym_seg0,
                                            d_quant, d_coef);
     return cudaGetLastError();
 }
@@ -537,17 +541,22 @@ cudaError_t launch_decode_fused(const EntropyJob& j, const int16_t* d_quant, voi
                                 uint32_t W, uint32_t H, const uint32_t* d_gop_first, uint32_t n_gops, void* d_state,
                                 cudaStream_t s) {
     if (n_frames == 0) return cudaSuccess;
-    static int n_sm[64] = {0};                                             // per device
+    // per-device set-up (dynamic shared memory opt-in, SM count): once per device, thread-safe
+    static std::once_flag once[64];
+    static int n_sm[64];
+    static cudaError_t status[64];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (!n_sm[dev]) {
-        if ((e = cudaFuncSetAttribute(k_decode_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_decode_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM)) != cudaSuccess) return e;
-        if ((e = cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        if (n_sm[dev] > FUSED_MAX_CTAS) n_sm[dev] = FUSED_MAX_CTAS;        // the scratch area is sized for this many
-    }
+    std::call_once(once[dev], [dev]() {
+        cudaError_t e2 = cudaFuncSetAttribute(k_decode_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_decode_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
+        if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (e2 == cudaSuccess && n_sm[dev] > FUSED_MAX_CTAS) n_sm[dev] = FUSED_MAX_CTAS;   // the scratch area is sized for this many
+        status[dev] = e2;
+    });
+    if (status[dev] != cudaSuccess) return status[dev];
     const uint32_t wb = W / 8, nb = wb * (H / 8);
     const uint64_t n_items = (uint64_t)((nb + 31) / 32) * (d_gop_first ? n_gops : n_frames);
     const uint64_t want = (n_items + FUSED_TPB / 32 - 1) / (FUSED_TPB / 32);

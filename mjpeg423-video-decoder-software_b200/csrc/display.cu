@@ -109,10 +109,10 @@ extern "C" int mjpeg423_b200_write_bmp(const char* path, const rgb_pixel_t* rgb,
 // frame, in display order, with the scanned-out buffer.  Returns the number of frames displayed or a negative
 // MJPEG423_E_* code; *dropped (optional) counts timer ticks that found no new frame (the reference's switch_frames
 // returning -1: the previous frame stays on screen).
-extern "C" long mjpeg423_b200_play(mjpeg423_b200_ctx* c, const uint8_t* mpg, size_t len, uint32_t first, uint32_t n,
-                                   mjpeg423_b200_display* d, uint32_t frame_period_us,
-                                   void (*on_display)(void* user, uint32_t frame_index, const rgb_pixel_t* frame), void* user,
-                                   uint32_t* dropped) {
+static long play_impl(mjpeg423_b200_ctx* c, const uint8_t* mpg, size_t len, uint32_t first, uint32_t n,
+                      mjpeg423_b200_display* d, uint32_t frame_period_us,
+                      void (*on_display)(void* user, uint32_t frame_index, const rgb_pixel_t* frame), void* user,
+                      uint32_t* dropped) {
     if (!c || !d || !mpg) return MJPEG423_E_ARG;
     mjpeg423_b200_info info;
     int rc = mjpeg423_b200_probe(mpg, len, &info);
@@ -170,4 +170,10 @@ extern "C" long mjpeg423_b200_play(mjpeg423_b200_ctx* c, const uint8_t* mpg, siz
     d_frames.release();
     if (dropped) *dropped = misses;
     return (long)displayed;
+}
+extern "C" long mjpeg423_b200_play(mjpeg423_b200_ctx* c, const uint8_t* mpg, size_t len, uint32_t first, uint32_t n,
+                                   mjpeg423_b200_display* d, uint32_t frame_period_us,
+                                   void (*on_display)(void* user, uint32_t frame_index, const rgb_pixel_t* frame), void* user,
+                                   uint32_t* dropped) {
+    return mj::guard<long>([&]() -> long { return play_impl(c, mpg, len, first, n, d, frame_period_us, on_display, user, dropped); });
 }

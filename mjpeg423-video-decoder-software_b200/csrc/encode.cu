@@ -351,9 +351,9 @@ extern "C" size_t mjpeg423_b200_encode_bound(uint32_t n, uint32_t w_size, uint32
     return 20 + (size_t)n * (16 + 3 * nb * 160 + 4 + 8) + 512;       // <= 1212 bits per block, SURVEY.md A.6
 }
 
-extern "C" int mjpeg423_b200_encode_frames(mjpeg423_b200_ctx* c, const void* frames, int frames_on_device, uint32_t n,
-                                           uint32_t W, uint32_t H, uint32_t max_I_interval, uint32_t flags,
-                                           uint8_t* mpg, size_t cap, size_t* mpg_len) {
+static int encode_frames_impl(mjpeg423_b200_ctx* c, const void* frames, int frames_on_device, uint32_t n,
+                              uint32_t W, uint32_t H, uint32_t max_I_interval, uint32_t flags,
+                              uint8_t* mpg, size_t cap, size_t* mpg_len) {
     if (!c || !mpg || !mpg_len || (n && !frames)) return MJPEG423_E_ARG;
     if (!W || !H || (W & 7) || (H & 7)) { set_error("encode: W and H must be non-zero multiples of 8"); return MJPEG423_E_ARG; }
     CUE(cudaSetDevice(c->device));
@@ -448,4 +448,9 @@ extern "C" int mjpeg423_b200_encode_frames(mjpeg423_b200_ctx* c, const void* fra
     c->stats.payload_bytes = pos;
     *mpg_len = pos;
     return MJPEG423_OK;
+}
+extern "C" int mjpeg423_b200_encode_frames(mjpeg423_b200_ctx* c, const void* frames, int frames_on_device, uint32_t n,
+                                           uint32_t W, uint32_t H, uint32_t max_I_interval, uint32_t flags,
+                                           uint8_t* mpg, size_t cap, size_t* mpg_len) {
+    return mj::guard([&]() -> int { return encode_frames_impl(c, frames, frames_on_device, n, W, H, max_I_interval, flags, mpg, cap, mpg_len); });
 }

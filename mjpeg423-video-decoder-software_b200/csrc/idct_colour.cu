@@ -12,6 +12,8 @@
 // row reads (LDS.128 at a 128-byte stride) are bank-conflict free.  The IDCT runs entirely in registers
 // (int32, reference operation order); pixels leave as one 256-bit store per block row, i.e. one full
 // 32-byte sector per lane and 1 KB contiguous per warp and row.
+#include <mutex>
+
 #include "common.cuh"
 #include "runtime.h"
 
@@ -75,9 +77,9 @@ k_idct(const int16_t* __restrict__ coef, uint8_t* __restrict__ samples, size_t n
 
 // ---- ycbcr_to_rgb(): sample planes (frame-major, Y|Cb|Cr, block-major) -> BGRA raster ---------------
 __global__ void __launch_bounds__(IDCT_TPB)
-k_colour(const uint8_t* __restrict__ samples, uint8_t* __restrict__ out, uint32_t nb, uint32_t wb, uint32_t W) {
-    const uint32_t f = blockIdx.y;
-    const uint32_t b = blockIdx.x * IDCT_TPB + threadIdx.x;
+k_colour(const uint8_t* __restrict__ samples, uint8_t* __restrict__ out, uint32_t nb, uint32_t wb, uint32_t W, uint32_t groups) {
+    const uint32_t f = blockIdx.x / groups;                  // (the frame index is folded into blockIdx.x: gridDim.y <= 65535)
+    const uint32_t b = (blockIdx.x - f * groups) * IDCT_TPB + threadIdx.x;
     if (b >= nb) return;
     const uint8_t* fs = samples + (size_t)f * 3 * nb * 64;
     const uint4* yp = reinterpret_cast<const uint4*>(fs + (size_t)b * 64);
@@ -94,11 +96,11 @@ k_colour(const uint8_t* __restrict__ samples, uint8_t* __restrict__ out, uint32_
 
 // ---- fused IDCT + colour: coefficient planes (frame-major, Y|Cb|Cr) -> BGRA raster ------------------
 __global__ void __launch_bounds__(IDCT_TPB, 4)
-k_idct_colour(const int16_t* __restrict__ coef, uint8_t* __restrict__ out, uint32_t nb, uint32_t wb, uint32_t W) {
+k_idct_colour(const int16_t* __restrict__ coef, uint8_t* __restrict__ out, uint32_t nb, uint32_t wb, uint32_t W, uint32_t groups) {
     extern __shared__ __align__(128) uint8_t smem[];          // 3 x TILE_BYTES
     const int t = threadIdx.x;
-    const uint32_t f = blockIdx.y;
-    const uint32_t b0 = blockIdx.x * IDCT_TPB;
+    const uint32_t f = blockIdx.x / groups;
+    const uint32_t b0 = (blockIdx.x - f * groups) * IDCT_TPB;
     const int nblk = (int)min((uint32_t)IDCT_TPB, nb - b0);
     const int16_t* fc = coef + (size_t)f * 3 * nb * 64;
 #pragma unroll
@@ -158,22 +160,28 @@ cudaError_t launch_colour(const uint8_t* d_samples, void* d_out, uint32_t n_fram
                           cudaStream_t s) {
     if (n_frames == 0) return cudaSuccess;
     uint32_t wb = W / 8, nb = wb * (H / 8);
-    dim3 grid((nb + IDCT_TPB - 1) / IDCT_TPB, n_frames);
-    k_colour<<<grid, IDCT_TPB, 0, s>>>(d_samples, (uint8_t*)d_out, nb, wb, W);
+    const uint32_t groups = (nb + IDCT_TPB - 1) / IDCT_TPB;
+    if ((uint64_t)groups * n_frames > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+    k_colour<<<groups * n_frames, IDCT_TPB, 0, s>>>(d_samples, (uint8_t*)d_out, nb, wb, W, groups);
     return cudaGetLastError();
 }
 cudaError_t launch_idct_colour(const int16_t* d_coef, void* d_out, uint32_t n_frames, uint32_t W, uint32_t H,
                                cudaStream_t s) {
     if (n_frames == 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_idct_colour, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static std::once_flag once[64];                      // per device, thread-safe
+    static cudaError_t status[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::call_once(once[dev], [dev]() {
+        status[dev] = cudaFuncSetAttribute(k_idct_colour, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_BYTES);
+    });
+    if (status[dev] != cudaSuccess) return status[dev];
     uint32_t wb = W / 8, nb = wb * (H / 8);
-    dim3 grid((nb + IDCT_TPB - 1) / IDCT_TPB, n_frames);
-    k_idct_colour<<<grid, IDCT_TPB, 3 * TILE_BYTES, s>>>(d_coef, (uint8_t*)d_out, nb, wb, W);
+    const uint32_t groups = (nb + IDCT_TPB - 1) / IDCT_TPB;
+    if ((uint64_t)groups * n_frames > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+    k_idct_colour<<<groups * n_frames, IDCT_TPB, 3 * TILE_BYTES, s>>>(d_coef, (uint8_t*)d_out, nb, wb, W, groups);
     return cudaGetLastError();
 }
 cudaError_t launch_hash_frames(const void* d_frames, uint64_t frame_bytes, uint32_t n, unsigned long long* d_hashes,
@@ -184,8 +192,12 @@ cudaError_t launch_hash_frames(const void* d_frames, uint64_t frame_bytes, uint3
     uint64_t words = frame_bytes / 8;
     uint64_t gx64 = (words + 255) / 256;
     unsigned gx = (unsigned)(gx64 < 64 ? gx64 : 64);
-    k_hash_frames<<<dim3(gx ? gx : 1, n), 256, 0, s>>>((const uint64_t*)d_frames, words, d_hashes);
-    return cudaGetLastError();
+    for (uint32_t f0 = 0; f0 < n; f0 += 65535u) {            // gridDim.y <= 65535
+        const uint32_t m = n - f0 < 65535u ? n - f0 : 65535u;
+        k_hash_frames<<<dim3(gx ? gx : 1, m), 256, 0, s>>>((const uint64_t*)d_frames + (size_t)f0 * words, words, d_hashes + f0);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace mj

@@ -191,6 +191,7 @@ extern "C" int mjpeg423_b200_device_count(void) {
 
 extern "C" const char* mjpeg423_b200_last_error(void) { return mj::last_error().c_str(); }
 
+extern "C" void mjpeg423_b200_destroy(mjpeg423_b200_ctx* c);
 extern "C" int mjpeg423_b200_create(mjpeg423_b200_ctx** out, int device) {
     if (!out) return MJPEG423_E_ARG;
     *out = nullptr;
@@ -204,16 +205,22 @@ extern "C" int mjpeg423_b200_create(mjpeg423_b200_ctx** out, int device) {
     }
     if (device < 0 || device >= ndev) { set_error("bad device ordinal"); return MJPEG423_E_ARG; }
     CU(cudaSetDevice(device));
-    mjpeg423_b200_ctx* c = new mjpeg423_b200_ctx();
+    mjpeg423_b200_ctx* c = new (std::nothrow) mjpeg423_b200_ctx();
+    if (!c) { set_error("out of host memory"); return MJPEG423_E_NOMEM; }
     c->device = device;
-    CU(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
-    for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
-    CU(cudaMalloc(&c->d_quant, sizeof(c->h_quant)));
+    auto init = [&]() -> int {                       // (everything created so far is released on any failure)
+        CU(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+        for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
+        CU(cudaMalloc(&c->d_quant, sizeof(c->h_quant)));
+        return mjpeg423_b200_set_quant(c, nullptr, nullptr);
+    };
+    const int rc = init();
+    if (rc != MJPEG423_OK) { mjpeg423_b200_destroy(c); return rc; }
     *out = c;
-    return mjpeg423_b200_set_quant(c, nullptr, nullptr);
+    return MJPEG423_OK;
 }
 
 extern "C" void mjpeg423_b200_destroy(mjpeg423_b200_ctx* c) {
@@ -256,12 +263,15 @@ extern "C" int mjpeg423_b200_set_quant(mjpeg423_b200_ctx* c, const int16_t* yq, 
     return MJPEG423_OK;
 }
 
-extern "C" int mjpeg423_b200_probe(const uint8_t* mpg, size_t len, mjpeg423_b200_info* info) {
+static int mjpeg423_b200_probe_impl(const uint8_t* mpg, size_t len, mjpeg423_b200_info* info) {
     if (!info) return MJPEG423_E_ARG;
     MpgIndex idx;
     int rc = parse_mpg(mpg, len, idx, false);
     *info = idx.info;
     return rc;
+}
+extern "C" int mjpeg423_b200_probe(const uint8_t* mpg, size_t len, mjpeg423_b200_info* info) {
+    return mj::guard([&]() -> int { return mjpeg423_b200_probe_impl(mpg, len, info); });
 }
 
 // ---- plan upload --------------------------------------------------------------------------------------
@@ -482,7 +492,7 @@ int finish_stats(mjpeg423_b200_ctx* c, const Plan& plan, const Tables& t, cudaSt
 
 }  // namespace
 
-extern "C" int mjpeg423_b200_upload(mjpeg423_b200_ctx* c, const uint8_t* mpg, size_t len, uint32_t first, uint32_t n) {
+static int mjpeg423_b200_upload_impl(mjpeg423_b200_ctx* c, const uint8_t* mpg, size_t len, uint32_t first, uint32_t n) {
     if (!c) return MJPEG423_E_ARG;
     CU(cudaSetDevice(c->device));
     c->have_plan = false;
@@ -503,8 +513,11 @@ extern "C" int mjpeg423_b200_upload(mjpeg423_b200_ctx* c, const uint8_t* mpg, si
     c->have_plan = true;
     return MJPEG423_OK;
 }
+extern "C" int mjpeg423_b200_upload(mjpeg423_b200_ctx* c, const uint8_t* mpg, size_t len, uint32_t first, uint32_t n) {
+    return mj::guard([&]() -> int { return mjpeg423_b200_upload_impl(c, mpg, len, first, n); });
+}
 
-extern "C" int mjpeg423_b200_decode_resident(mjpeg423_b200_ctx* c, void* d_out) {
+static int mjpeg423_b200_decode_resident_impl(mjpeg423_b200_ctx* c, void* d_out) {
     if (!c || !c->have_plan) { set_error("no resident job: call mjpeg423_b200_upload first"); return MJPEG423_E_ARG; }
     CU(cudaSetDevice(c->device));
     const Plan& plan = c->plan;
@@ -566,6 +579,9 @@ extern "C" int mjpeg423_b200_decode_resident(mjpeg423_b200_ctx* c, void* d_out) 
     c->stats.total_ms = ms;
     return rc;
 }
+extern "C" int mjpeg423_b200_decode_resident(mjpeg423_b200_ctx* c, void* d_out) {
+    return mj::guard([&]() -> int { return mjpeg423_b200_decode_resident_impl(c, d_out); });
+}
 
 extern "C" int mjpeg423_b200_get_stats(mjpeg423_b200_ctx* c, mjpeg423_b200_stats* s) {
     if (!c || !s) return MJPEG423_E_ARG;
@@ -575,7 +591,7 @@ extern "C" int mjpeg423_b200_get_stats(mjpeg423_b200_ctx* c, mjpeg423_b200_stats
 
 // ---- stage-level entry points on the resident job ------------------------------------------------------
 // lossless_decode() of every plane of every resident frame: d_coef = n x 3 x nb x 64 int16.
-extern "C" int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* c, int16_t* d_coef) {
+static int mjpeg423_b200_resident_entropy_impl(mjpeg423_b200_ctx* c, int16_t* d_coef) {
     if (!c || !c->have_plan || !d_coef) return MJPEG423_E_ARG;
     CU(cudaSetDevice(c->device));
     const Plan& plan = c->plan;
@@ -611,6 +627,9 @@ extern "C" int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* c, int16_t* d_c
     CU(cudaEventElapsedTime(&c->stats.index_ms, e[2], e[3]));
     CU(cudaEventElapsedTime(&c->stats.decode_ms, e[3], e[4]));
     return rc;
+}
+extern "C" int mjpeg423_b200_resident_entropy(mjpeg423_b200_ctx* c, int16_t* d_coef) {
+    return mj::guard([&]() -> int { return mjpeg423_b200_resident_entropy_impl(c, d_coef); });
 }
 
 namespace {
@@ -649,7 +668,7 @@ extern "C" int mjpeg423_b200_resident_idct_colour(mjpeg423_b200_ctx* c, const in
 }
 
 // ---- end-to-end path: host .mpg -> (host | device) frames, chunked and overlapped ----------------------
-extern "C" int mjpeg423_b200_decode_frames(mjpeg423_b200_ctx* c, const uint8_t* mpg, size_t len, uint32_t first,
+static int mjpeg423_b200_decode_frames_impl(mjpeg423_b200_ctx* c, const uint8_t* mpg, size_t len, uint32_t first,
                                            uint32_t n, void* out, int out_on_device) {
     if (!c) return MJPEG423_E_ARG;
     CU(cudaSetDevice(c->device));
@@ -723,6 +742,10 @@ extern "C" int mjpeg423_b200_decode_frames(mjpeg423_b200_ctx* c, const uint8_t* 
     CU(cudaEventElapsedTime(&ms, ev_start, ev_stop));
     c->stats.total_ms = ms;
     return rc;
+}
+extern "C" int mjpeg423_b200_decode_frames(mjpeg423_b200_ctx* c, const uint8_t* mpg, size_t len, uint32_t first,
+                                           uint32_t n, void* out, int out_on_device) {
+    return mj::guard([&]() -> int { return mjpeg423_b200_decode_frames_impl(c, mpg, len, first, n, out, out_on_device); });
 }
 
 // ---- memory helpers ------------------------------------------------------------------------------------

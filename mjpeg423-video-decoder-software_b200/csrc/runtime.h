@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -91,6 +93,21 @@ void make_chunks(const Plan& plan, uint32_t K, std::vector<Chunk>& chunks, std::
 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
+
+// No C++ exception may cross the C boundary (a crafted header must not end the host process in std::terminate):
+// every extern "C" entry that allocates host memory runs its body through guard().
+template <class R = int, class F>
+R guard(F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        set_error("out of host memory");
+        return (R)MJPEG423_E_NOMEM;
+    } catch (const std::exception& e) {
+        set_error(std::string("internal error: ") + e.what());
+        return (R)MJPEG423_E_ARG;
+    }
+}
 
 }  // namespace mj
 
