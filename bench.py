@@ -14,9 +14,13 @@ region.  Frames are independent intra frames, so ranks shard by frame range with
 ("weak": every rank decodes its own `frames` frames; the 1080p-8192 workload is the fixed-total variant).
 --gather additionally moves every rank's frames into ONE contiguous buffer on rank 0 (NCCL point-to-point over
 NVLink, SURVEY.md 8e "optional single contiguous output"), timed on its own and reported under "gather".
-The JSON line also carries "roofline" (dominant kernel: algorithmic bytes / its measured time vs the measured HBM
-peak), "stages" (every kernel the same way), "cpu_baseline" (N=1: the compiled reference on all host cores, bounded
-sample), "clocks" (nvidia-smi samples inside the timed region) and "gpu_launches".
+The JSON line also carries "roofline" (dominant kernel: the ALGORITHMIC bytes of SURVEY.md 8d, C + 4P per frame, over
+its measured time vs the measured HBM peak; the symbol lists and the block index it really moves are reported as
+"intermediate_bytes"), "stages" (every kernel with the bytes it moves), "stages_staged" (the IDCT / colour stage kernels
+of the staged modes: 9P / 7P / 10P), "extra" (the other BASELINE configurations, each verified on its own: 4K dense =
+configs[3]; the 8192-frame 1080p batch sharded over the ranks = configs[4], strong scaling), "host_link" (plain pinned
+D2H copy bandwidth, all ranks at once: the ceiling of e2e), "cpu_baseline" (N=1: the compiled reference, one pinned
+process per host core, >= 3 s), "clocks" (nvidia-smi samples inside the timed region) and "gpu_launches".
 
 Prints ONE JSON line on rank 0.
 """
@@ -200,35 +204,104 @@ def make_stream(wl: str, frames: int, nthreads: int):
     return mpg, uniq, q
 
 
+def workload_config(wl: str, frames: int, world: int) -> dict:
+    """The keys that NAME the workload: identical in the b200 arm and the reference arm."""
+    W, H, _, uniq, amp, quant, strong = WORKLOADS[wl]
+    return {"workload": wl, "width": W, "height": H, "frames_total" if strong else "frames_per_gpu": frames,
+            "unique_pictures": min(uniq, frames), "noise_amp": amp, "quant": quant,
+            "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"frame-range x{world}, no collective"}
+
+
+def _cpu_worker(job):
+    """One host process of the CPU baseline: pinned to one core, decodes its contiguous frame range `reps` times."""
+    cpu, lo, hi, reps, quant_ones, barrier, mpg = job
+    try:
+        os.sched_setaffinity(0, {cpu})
+    except Exception:
+        pass
+    from oracle import oracle
+    chk = oracle.best()
+    q = np.ones(64, np.int16) if quant_ones else None
+    secs = np.zeros(3)
+    chk.decode_mpg(mpg, lo, 1, yq=q, cq=q)                 # page the library and the stream in
+    barrier.wait()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        chk.decode_mpg(mpg, lo, hi - lo, yq=q, cq=q, nthreads=1, stage_secs=secs)
+    return t0, time.perf_counter(), (hi - lo) * reps, secs
+
+
+_CPU_JOBS = None
+
+
+def _cpu_worker_idx(k):
+    return _cpu_worker(_CPU_JOBS[k])
+
+
+def cpu_reference_fps(mpg: np.ndarray, n_frames: int, quant_ones: bool, min_seconds: float, per_core_fps: float):
+    """the reference decode functions, one PROCESS per host core, each pinned
+    (sched_setaffinity) and given a contiguous frame range of the same in-memory stream; wall time from the first start
+    to the last finish.  Must run before this process touches CUDA (the workers are forked)."""
+    global _CPU_JOBS
+    import multiprocessing as mp
+    cpus = sorted(os.sched_getaffinity(0))
+    cores = len(cpus)
+    per = max(1, n_frames // cores)
+    reps = max(1, int(np.ceil(min_seconds * per_core_fps / per)))
+    ctx = mp.get_context("fork")
+    barrier = ctx.Barrier(cores)
+    _CPU_JOBS = [(cpus[k], k * per, (k + 1) * per, reps, quant_ones, barrier, mpg) for k in range(cores)]   # inherited by fork
+    procs_out = ctx.Queue()
+
+    def run(k):
+        procs_out.put(_cpu_worker(_CPU_JOBS[k]))
+    procs = [ctx.Process(target=run, args=(k,)) for k in range(cores)]
+    for pr in procs:
+        pr.start()
+    res = [procs_out.get() for _ in procs]
+    for pr in procs:
+        pr.join()
+    t0, t1 = min(r[0] for r in res), max(r[1] for r in res)
+    frames = sum(r[2] for r in res)
+    secs = np.sum([r[3] for r in res], axis=0)
+    from oracle import oracle
+    return {"value": frames / (t1 - t0), "unit": "frames/s", "cores": cores, "kind": oracle.best().kind,
+            "sample": f"{cores} pinned processes x {per} frames x {reps} passes of the same stream "
+                      f"(contiguous frame range each), {t1 - t0:.2f} s wall",
+            "per_core": frames / (t1 - t0) / cores,
+            "stage_share": {k: float(v / secs.sum()) for k, v in zip(("entropy", "idct", "colour"), secs)}}
+
+
+PER_CORE_FPS = {"480p": 170.0, "1080p": 21.0, "4k": 4.0, "4k-q1": 3.0, "1080p-8192": 21.0}
+
+
 def reference_arm(args, rank: int, world: int):
     """The reference's own lossless_decode/idct/ycbcr_to_rgb (oracle/_ref, compiled from /root/reference)
     or, if that did not travel, the C restatement -- on all host cores, bounded sample per step."""
     if rank != 0:
         return
-    from oracle import oracle
-    chk = oracle.best()
-    W, H, _, uniq, amp, quant, _ = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    fps_guess = {"480p": 170.0, "1080p": 21.0, "4k": 4.0, "4k-q1": 3.0, "1080p-8192": 21.0}[args.workload] * cores
-    n = int(max(cores, min(64 * 8, fps_guess * args.ref_seconds)))
-    mpg, uniq, q = make_stream(args.workload, n, cores)
-    for _ in range(args.warmup):
-        chk.decode_mpg(mpg, 0, min(n, cores), yq=q, cq=q, nthreads=cores)
-    stage = np.zeros(3)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        chk.decode_mpg(mpg, 0, n, yq=q, cq=q, nthreads=cores, stage_secs=stage)
-    dt = time.perf_counter() - t0
-    fps = n * args.steps / dt
-    sample = f"{n} frames {W}x{H} per step ({uniq} unique pictures cycled), {cores} threads, contiguous frame range each"
+    W, H, frames, uniq, amp, quant, _ = WORKLOADS[args.workload]
+    if args.frames:
+        frames = args.frames
+    cores = len(os.sched_getaffinity(0))
+    per = max(2, int(np.ceil(PER_CORE_FPS[args.workload])))                 # frames per process and pass (~1 s)
+    n = per * cores
+    mpg, uniq_n, q = make_stream(args.workload, n, cores)
+    runs = []
+    for i in range(args.warmup + args.steps):                   # a step = every core decoding its range for ref_seconds
+        r = cpu_reference_fps(mpg, n, q is not None, args.ref_seconds, PER_CORE_FPS[args.workload])
+        if i >= args.warmup:
+            runs.append(r)
+    fps = float(np.mean([r["value"] for r in runs]))
+    cb = dict(runs[-1])
+    cb["value"] = fps
     line = {
         "impl": "reference", "metric": "decoded frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": args.workload, "width": W, "height": H, "frames_per_step": n, "noise_amp": amp,
-                   "quant": quant, "host": "cpu"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": chk.kind, "sample": sample,
-                         "stage_share": {k: float(v / stage.sum()) for k, v in zip(("entropy", "idct", "colour"), stage)}},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean([n / r["value"] for r in runs])) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args.workload, frames, args.gpus),
+        "details": {"host": "cpu", "sample_frames": n, "sample_unique_pictures": uniq_n},
+        "cpu_baseline": cb,
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -378,6 +451,45 @@ def encoder_bench(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+def run_config(dec, wl: str, my_frames: int, steps: int, warmup: int, verify: bool, gen_threads: int, barrier):
+    """One extra BASELINE configuration on this rank: stream resident in HBM, every frame verified through the 64-bit
+    position-mixed checksum against the oracle, then `steps` timed decode_resident() calls (CUDA events of the library)."""
+    from mjpeg423_b200 import api
+    W, H = WORKLOADS[wl][0], WORKLOADS[wl][1]
+    mpg, uniq, q = make_stream(wl, my_frames, gen_threads)
+    frame_bytes = W * H * 4
+    if q is not None:
+        dec.set_quant(q, q)
+    dec.upload(mpg)
+    d_out = dec.device_alloc(my_frames * frame_bytes)
+    verified = None
+    try:
+        if verify:
+            from oracle import oracle
+            chk = oracle.best()
+            dec.decode_resident(d_out)
+            got = dec.hash_frames(d_out, frame_bytes, my_frames)
+            want = api.frame_hash_host(chk.decode_mpg(mpg, 0, uniq, yq=q, cq=q, nthreads=gen_threads))[np.arange(my_frames) % uniq]
+            if not np.array_equal(got, want):
+                raise SystemExit(f"{wl}: frame {int(np.flatnonzero(got != want)[0])} differs from the {chk.kind} oracle")
+            verified = f"{my_frames} frames/rank: per-frame 64-bit checksum == {chk.kind} oracle"
+        for _ in range(warmup):
+            dec.decode_resident(d_out)
+        barrier()
+        ev_ms = 0.0
+        for _ in range(steps):
+            dec.decode_resident(d_out)
+            ev_ms += dec.stats()["total_ms"]
+        barrier()
+        st = dec.stats()
+    finally:
+        dec.device_free(d_out)
+        if q is not None:
+            dec.set_quant(None, None)
+    return {"ev_ms": ev_ms, "frames": my_frames, "verified": verified, "payload_bytes": st["payload_bytes"],
+            "fixups": st["fixups"], "W": W, "H": H}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -391,6 +503,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-seconds of work for the cpu_baseline sample")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra BASELINE configurations (4K dense, 8192-frame strong)")
     ap.add_argument("--gather", action="store_true",
                     help="multi-GPU: also gather every rank's frames into one contiguous buffer on rank 0 over NCCL (timed separately)")
     args = ap.parse_args()
@@ -406,6 +519,19 @@ def main():
         reference_arm(args, rank, world)
         return
 
+    W, H, frames, uniq, amp, quant, strong = WORKLOADS[args.workload]
+    if args.frames:
+        frames = args.frames
+    cores = os.cpu_count() or 1
+    # ---- CPU baseline first: it forks one pinned process per core, which must happen before CUDA is initialised ----
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        per = max(2, int(np.ceil(PER_CORE_FPS[args.workload])))
+        ncores = len(os.sched_getaffinity(0))
+        mpg_cpu, _, q_cpu = make_stream(args.workload, per * ncores, ncores)
+        cpu_baseline = cpu_reference_fps(mpg_cpu, per * ncores, q_cpu is not None, max(3.0, args.cpu_seconds / 4), PER_CORE_FPS[args.workload])
+        del mpg_cpu
+
     import torch
     import torch.distributed as dist
 
@@ -419,16 +545,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    W, H, frames, uniq, amp, quant, strong = WORKLOADS[args.workload]
-    if args.frames:
-        frames = args.frames
     if strong:
         lo, hi = shard_range(frames, rank, world)
         my_frames = hi - lo
     else:
         my_frames = frames
     binding = bind_near_gpu(local_rank) if world > 1 else None
-    cores = os.cpu_count() or 1
     mpg, uniq, q = make_stream(args.workload, my_frames, max(1, cores // world))
     frame_bytes = W * H * 4
     P = W * H
@@ -549,9 +671,56 @@ def main():
                       "verified": ok}
         del full
 
+    # ---- the stage kernels of the staged modes (IDCT 9P, colour 7P; fused IDCT + colour 10P) --------------
+    n_st = int(min(my_frames, 256))
+    staged = {}
+    dec.upload(mpg, 0, n_st)
+    dec.set_option(api.OPT_PROFILE, 1)
+    for mode in (2, 1):
+        dec.set_option(api.OPT_STAGED, mode)
+        dec.decode_resident(d_out)
+        dec.decode_resident(d_out)
+        st2 = dec.stats()
+        if mode == 2:
+            staged["k_idct"] = {"ms": st2["idct_ms"], "bytes": 9 * P * n_st}
+            staged["k_colour"] = {"ms": st2["colour_ms"], "bytes": 7 * P * n_st}
+            staged["k_decode_coef"] = {"ms": st2["decode_ms"], "bytes": 6 * P * n_st + 4 * st2["list_entries"]}
+        else:
+            staged["k_idct_colour"] = {"ms": st2["idct_colour_ms"], "bytes": 10 * P * n_st}
+    dec.set_option(api.OPT_STAGED, 0)
+    dec.set_option(api.OPT_PROFILE, 0)
+    if not args.no_verify:
+        assert np.array_equal(dec.hash_frames(d_out, frame_bytes, n_st), want[:n_st]), "staged modes differ from the oracle"
+
+    # ---- the host link: plain device -> pinned-host copies, every rank at once (what bounds e2e) ----------------------
+    link_bytes = 1 << 30
+    lt_d = torch.empty(link_bytes, dtype=torch.uint8, device="cuda")
+    lt_h = torch.empty(link_bytes, dtype=torch.uint8).pin_memory()
+    lt_h.copy_(lt_d, non_blocking=True)
+    barrier()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
+    for _ in range(4):
+        lt_h.copy_(lt_d, non_blocking=True)
+    l1.record()
+    barrier()
+    link_ms = l0.elapsed_time(l1) / 4
+    del lt_d, lt_h
+
+    # ---- the other BASELINE configurations, each verified on its own ------------------------------------------------
+    extras = {}
+    if not args.no_extra and args.workload == "1080p" and not (args.gather and world > 1):
+        dec.device_free(d_out)
+        d_out = None
+        gen_threads = max(1, cores // world)
+        extras["4k"] = run_config(dec, "4k", 128, 5, 2, not args.no_verify, gen_threads, barrier)           # configs[3], weak
+        lo8, hi8 = shard_range(WORKLOADS["1080p-8192"][2], rank, world)
+        extras["1080p-8192"] = run_config(dec, "1080p-8192", hi8 - lo8, 3, 1, not args.no_verify, gen_threads, barrier)   # configs[4]
+
     # ---- reduce over ranks ----------------------------------------------------------------------------------------
-    (ev_ms_max, wall_ms_max, e2e_s_max), (total_frames, total_launches, total_e2e_frames) = reduce_over_ranks(
-        dist, [ev_ms, wall_ms, e2e_s], [my_frames, launches, e2e_frames], "cuda")
+    (ev_ms_max, wall_ms_max, e2e_s_max, link_ms_max, x4k_ms, x8k_ms), (total_frames, total_launches, total_e2e_frames, x4k_fr, x8k_fr) = reduce_over_ranks(
+        dist, [ev_ms, wall_ms, e2e_s, link_ms, extras.get("4k", {}).get("ev_ms", 0.0), extras.get("1080p-8192", {}).get("ev_ms", 0.0)],
+        [my_frames, launches, e2e_frames, extras.get("4k", {}).get("frames", 0), extras.get("1080p-8192", {}).get("frames", 0)], "cuda")
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -583,47 +752,62 @@ def main():
                 traffic = cap["dram_bytes_per_frame"] * n
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": stage[dom]["kernels"], "achieved": stage[dom]["GBs"], "peak": peak,
-                    "unit": "GB/s", "frac": stage[dom]["GBs"] / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_step": stage[dom]["bytes"], "step_ms_in_kernel": stage[dom]["ms"],
+        # The roofline number uses the ALGORITHMIC bytes of SURVEY.md 8d -- read the bitstream once, write BGRA once:
+        # (C + 4P) per frame -- over the dominant kernel's measured time; what the kernel really moves (symbol lists and
+        # block index on top of its pixels) is reported beside it.
+        alg = (Cbar + 4 * P) * n
+        ach = alg / max(stage[dom]["ms"], 1e-9) / 1e6
+        roofline = {"bound": "hbm", "kernel": stage[dom]["kernels"], "achieved": ach, "peak": peak,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_step": alg, "algorithmic_bytes_per_frame": Cbar + 4 * P,
+                    "intermediate_bytes": {"moved_by_kernel_per_step": stage[dom]["bytes"], "symbol_lists_per_step": lists,
+                                           "block_index_per_step": 8 * blocks},
+                    "step_ms_in_kernel": stage[dom]["ms"],
                     "launches_per_step": ps["kernel_launches"] // 5,     # one per pipeline chunk
                     "pipeline_headline": {"bytes_per_frame": Cbar + 4 * P, "GBs": fps / world * (Cbar + 4 * P) / 1e9,
                                           "frac": fps / world * (Cbar + 4 * P) / 1e9 / peak}}
-        cpu_baseline = None
-        if not args.no_cpu_baseline and world == 1:
-            from oracle import oracle
-            chk = oracle.best()
-            est = {"480p": 170.0, "1080p": 21.0, "4k": 4.0, "4k-q1": 3.0, "1080p-8192": 21.0}[args.workload]
-            ncpu = int(max(cores, min(my_frames, est * args.cpu_seconds)))
-            secs = np.zeros(3)
-            t0 = time.perf_counter()
-            chk.decode_mpg(mpg, 0, ncpu, yq=q, cq=q, nthreads=cores, stage_secs=secs)
-            dt = time.perf_counter() - t0
-            cpu_baseline = {"value": ncpu / dt, "unit": "frames/s", "cores": cores, "kind": chk.kind,
-                            "sample": f"first {ncpu} frames of the same stream, {cores} threads, contiguous frame range each, "
-                                      f"{dt:.2f} s wall",
-                            "per_core": ncpu / secs.sum(),
-                            "stage_share": {k: float(v / secs.sum()) for k, v in zip(("entropy", "idct", "colour"), secs)}}
+        for v in staged.values():
+            v["frames"] = n_st
+            v["GBs"] = v["bytes"] / max(v["ms"], 1e-9) / 1e6
+            v["frac_of_hbm_peak"] = v["GBs"] / peak
+        extra = {}
+        for key, ms_max, fr_tot, steps_x in (("4k", x4k_ms, x4k_fr, 5), ("1080p-8192", x8k_ms, x8k_fr, 3)):
+            if key not in extras:
+                continue
+            e = extras[key]
+            cb = e["payload_bytes"] / e["frames"]
+            px = e["W"] * e["H"]
+            xfps = fr_tot * steps_x / (ms_max / 1e3)
+            extra[key] = {"config": workload_config(key, int(fr_tot) if WORKLOADS[key][6] else e["frames"], world),
+                          "metric": "decoded frames/sec", "value": xfps, "unit": "frames/s", "steps": steps_x,
+                          "ms_per_step": ms_max / steps_x, "scaling": "strong" if WORKLOADS[key][6] else "weak",
+                          "compressed_bytes_per_frame": cb, "bits_per_pixel": 8 * cb / px, "chain_fixups": e["fixups"],
+                          "pipeline_headline": {"bytes_per_frame": cb + 4 * px, "GBs": xfps / world * (cb + 4 * px) / 1e9,
+                                                "frac": xfps / world * (cb + 4 * px) / 1e9 / peak},
+                          "verified": e["verified"]}
         line = {
             "metric": "decoded frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": args.workload, "width": W, "height": H, "frames_per_gpu": my_frames,
-                       "unique_pictures": uniq, "noise_amp": amp, "quant": quant,
-                       "compressed_bytes_per_frame": Cbar, "bits_per_pixel": 8 * Cbar / P,
-                       "l2": "inputs larger than L2 (bitstream %.0f MB, output %.1f GB per GPU per step)" %
-                             (payload_bytes / 1e6, my_frames * frame_bytes / 1e9),
-                       "parallelism": f"frame-range x{world}, no collective", "timing": "cuda events, max over ranks",
-                       "cpu_binding": binding,
-                       "wall_ms_per_step": wall_ms_max / args.steps, "verified": verified},
+            "config": workload_config(args.workload, frames, world),
+            "details": {"frames_this_rank": my_frames, "compressed_bytes_per_frame": Cbar, "bits_per_pixel": 8 * Cbar / P,
+                        "l2": "inputs larger than L2 (bitstream %.0f MB, output %.1f GB per GPU per step)" %
+                              (payload_bytes / 1e6, my_frames * frame_bytes / 1e9),
+                        "timing": "cuda events, max over ranks", "cpu_binding": binding,
+                        "wall_ms_per_step": wall_ms_max / args.steps, "verified": verified},
             "clocks": clocks,
             "e2e": {"value": total_e2e_frames * e2e_steps / e2e_s_max, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(e2e_frames * frame_bytes), "frames_per_step": e2e_frames, "steps": e2e_steps,
                     "GBs_d2h": total_e2e_frames / world * e2e_steps * frame_bytes / e2e_s_max / 1e9,
                     "api": "mjpeg423_b200_decode_frames (pinned host in/out)"},
+            "host_link": {"what": "plain device -> pinned host copies of 1 GiB, all ranks at once (no kernels)",
+                          "d2h_GBs_per_gpu": link_bytes / link_ms_max / 1e6, "d2h_GBs_aggregate": world * link_bytes / link_ms_max / 1e6,
+                          "e2e_share_of_link": (total_e2e_frames / world * e2e_steps * frame_bytes / e2e_s_max / 1e9) / (link_bytes / link_ms_max / 1e6)},
             "gpu_launches": int(total_launches),
             "roofline": roofline,
             "stages": stage,
+            "stages_staged": staged,
+            "extra": extra,
             "segments": {"per_step": ps["segments"], "chain_fixups": ps["fixups"]},
             "cpu_baseline": cpu_baseline,
         }
@@ -632,7 +816,7 @@ def main():
         print(json.dumps(line), flush=True)
     pin_in.free()
     pin_out.free()
-    if out_t is None:
+    if out_t is None and d_out is not None:
         dec.device_free(d_out)
     dec.close()
     if world > 1:
