@@ -125,7 +125,9 @@ k_decode_coef(const StreamDesc* __restrict__ streams, const uint32_t* __restrict
 // memory, not as one unrolled register-resident IDCT: warps drift apart in the data-dependent scatter,
 // so the instruction working set has to fit the instruction cache (the unrolled form is ~100 KB of
 // SASS and ran instruction-fetch bound, profiles/r01b).  Shared memory, in 16-byte granules interleaved
-// by thread (granule g of thread t at (g*T + t)*16, T = FUSED_TPB; conflict-free for 128-bit access):
+// by thread (granule g of thread t at (g*(T+1) + t)*16, T = FUSED_TPB; conflict-free for 128-bit access; the extra
+// granule per row rotates the banks by 4 from row to row: without it all columns of a block's slot share their banks
+// and the data-dependent scatter ran at 21 % conflicted wavefronts, with it at 10-15 %, profiles/r02i):
 //   ws    granules 0..15   granule cp*4 + r/2 = pass-1 outputs {ws[r][2cp], ws[r][2cp+1], ws[r+1][2cp], ws[r+1][2cp+1]}
 //   coef  granules 8..15   granule 8+c = column c of the block, rows 0..7 as int16.  ALIASES the upper half of
 //                          ws: pass 1 consumes columns 2cp, 2cp+1 in iteration cp and only then writes granules
@@ -134,7 +136,11 @@ k_decode_coef(const StreamDesc* __restrict__ streams, const uint32_t* __restrict
 //                          pass 1 reads a column with one LDS.128.)
 //   stash words [32][T]    word p*16 + 2r + h = samples of plane p (Y, Cb), row r, half h
 constexpr int FUSED_TPB = 576;                                   // 18 warps x 384 B/thread = 216 KB of the SM's 227 KB
-constexpr int FUSED_SMEM = FUSED_TPB * (256 + 128) + 2 * 64 * 8 + 16;     // + the CTA's tile counter
+constexpr int FUSED_ROW = FUSED_TPB + 1;                         // granules per workspace row: the odd granule rotates the banks by 4 from
+                                                                 // row to row, so a block's entries in different COLUMNS (rows FUSED_ROW * 16
+                                                                 // bytes apart) no longer meet in one bank when they are scattered
+constexpr int FUSED_OFF_STASH = 16 * FUSED_ROW * 16, FUSED_OFF_ZQ = FUSED_OFF_STASH + FUSED_TPB * 128;
+constexpr int FUSED_SMEM = FUSED_OFF_ZQ + 2 * 64 * 8 + 16;       // + the CTA's tile counter
 
 // PF = true is the variant for ranges that hold P frames (LIB/decoder/lossless_decode.c:90-92,121-123: every decoded
 // value is ADDED to the previous frame's coefficient).  A work item is then (tile, GOP): the warp walks the GOP's frames
@@ -150,16 +156,16 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                uint32_t n_frames, const uint32_t* __restrict__ gop_first, uint32_t n_gops, uint4* __restrict__ state) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint4* s_ws = reinterpret_cast<uint4*>(smem);                                   // granules 0..15
-    uint8_t* s_coef = smem + 8 * FUSED_TPB * 16;                                    // granules 8..15
-    uint32_t* s_stash = reinterpret_cast<uint32_t*>(smem + FUSED_TPB * 256);
-    uint2* s_zq = reinterpret_cast<uint2*>(smem + FUSED_TPB * 384);                 // 2 x 64 entries
-    uint32_t* s_next = reinterpret_cast<uint32_t*>(smem + FUSED_TPB * 384 + 1024);  // tiles handed out so far
+    uint8_t* s_coef = smem + 8 * FUSED_ROW * 16;                                    // granules 8..15
+    uint32_t* s_stash = reinterpret_cast<uint32_t*>(smem + FUSED_OFF_STASH);
+    uint2* s_zq = reinterpret_cast<uint2*>(smem + FUSED_OFF_ZQ);                 // 2 x 64 entries
+    uint32_t* s_next = reinterpret_cast<uint32_t*>(smem + FUSED_OFF_ZQ + 1024);  // tiles handed out so far
     const int t = threadIdx.x;
     if (t == 0) *s_next = 0u;
     if (t < 128) {     // zig-zag index -> .x = transposed slot offset | quant << 16, .y = column bit | (row >= 1) column bit << 8
         const int tab = t >> 6, k = t & 63;
         const uint32_t n = c_zigzag[k], col = n & 7u, row = n >> 3;
-        s_zq[t] = make_uint2((col * (FUSED_TPB * 16u) + row * 2u) | ((uint32_t)(uint16_t)quant[tab * 64 + n] << 16),
+        s_zq[t] = make_uint2((col * (FUSED_ROW * 16u) + row * 2u) | ((uint32_t)(uint16_t)quant[tab * 64 + n] << 16),
                              (1u << col) | ((row ? 1u : 0u) << (8 + col)));
     }
     __syncthreads();
@@ -394,12 +400,12 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                     const uint32_t sa = (uint32_t)__cvta_generic_to_shared(my_coef);
 #pragma unroll
                     for (int c = 0; c < 8; c++)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + c * (FUSED_TPB * 16)),
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + c * (FUSED_ROW * 16)),
                                      "l"(my_state + (p * 8 + c) * 32) : "memory");
                     asm volatile("cp.async.wait_all;" ::: "memory");
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(my_coef + c * (FUSED_TPB * 16)) = make_uint4(0, 0, 0, 0);
+                    for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(my_coef + c * (FUSED_ROW * 16)) = make_uint4(0, 0, 0, 0);
                 }
                 *reinterpret_cast<int16_t*>(my_coef) = (int16_t)dc_coef;
                 __syncwarp();
@@ -435,7 +441,7 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                         const uint32_t* src = sym + a + lane;
                         const uint32_t ng = (n + 127u) >> 7;              // pieces of 128 entries
                         for (uint32_t g = 0; g < ng; g++) {
-                            const uint32_t sa = stage0 + g * (FUSED_TPB * 16u), k = g * 128u + lane;
+                            const uint32_t sa = stage0 + g * (FUSED_ROW * 16u), k = g * 128u + lane;
 #pragma unroll
                             for (int i = 0; i < 4; i++)
                                 if (k + 32u * i < n)
@@ -443,7 +449,7 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                         }
                         asm volatile("cp.async.wait_all;" ::: "memory");
                         for (uint32_t g = 0; g < ng; g++) {
-                            const uint32_t sa = stage0 + g * (FUSED_TPB * 16u), k = g * 128u + lane;
+                            const uint32_t sa = stage0 + g * (FUSED_ROW * 16u), k = g * 128u + lane;
                             uint32_t ent[4];
 #pragma unroll
                             for (int i = 0; i < 4; i++)
@@ -468,7 +474,7 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                     if (has_ac && cur.f + 1u < cur.fend && (m_all & 0xFFFEu)) {   // park the slots for the item's next frame
 #pragma unroll
                         for (int c = 0; c < 8; c++)
-                            my_state[(p * 8 + c) * 32] = *reinterpret_cast<const uint4*>(my_coef + c * (FUSED_TPB * 16));
+                            my_state[(p * 8 + c) * 32] = *reinterpret_cast<const uint4*>(my_coef + c * (FUSED_ROW * 16));
                     }
                 }
             }
@@ -488,8 +494,8 @@ k_decode_fused(const uint2* __restrict__ blk_info,
             const int npair = high_half ? 4 : 2;
 #pragma unroll 2                 // (two pairs = four butterflies in flight; within a pair of iterations no store hits a later load)
             for (int cp = 0; cp < npair; cp++) {
-                const uint4 c0 = *reinterpret_cast<const uint4*>(my_coef + (2 * cp) * (FUSED_TPB * 16));
-                const uint4 c1 = *reinterpret_cast<const uint4*>(my_coef + (2 * cp + 1) * (FUSED_TPB * 16));
+                const uint4 c0 = *reinterpret_cast<const uint4*>(my_coef + (2 * cp) * (FUSED_ROW * 16));
+                const uint4 c1 = *reinterpret_cast<const uint4*>(my_coef + (2 * cp + 1) * (FUSED_ROW * 16));
                 int o0[8], o1[8];
                 if ((acm >> (2 * cp)) & 3u) {
                     idct8<11>(lo16(c0.x), hi16(c0.x), lo16(c0.y), hi16(c0.y), lo16(c0.z), hi16(c0.z), lo16(c0.w), hi16(c0.w), o0);
@@ -501,16 +507,16 @@ k_decode_fused(const uint2* __restrict__ blk_info,
                 }
 #pragma unroll
                 for (int r = 0; r < 8; r += 2)                   // both column loads above precede these stores (aliasing)
-                    s_ws[(cp * 4 + r / 2) * FUSED_TPB + t] = make_uint4((uint32_t)o0[r], (uint32_t)o1[r], (uint32_t)o0[r + 1], (uint32_t)o1[r + 1]);
+                    s_ws[(cp * 4 + r / 2) * FUSED_ROW + t] = make_uint4((uint32_t)o0[r], (uint32_t)o1[r], (uint32_t)o0[r + 1], (uint32_t)o1[r + 1]);
             }
             // ---- pass 2: rows (idct.c:116-180) ------------------------------------------------------------------
 #pragma unroll 1
             for (int r = 0; r < 8; r += 2) {                          // two rows per iteration: one LDS.128 per column pair
-                const uint4* g = s_ws + (r >> 1) * FUSED_TPB + t;      // and two independent butterflies in flight
-                const uint4 a = g[0], bq = g[4 * FUSED_TPB];
+                const uint4* g = s_ws + (r >> 1) * FUSED_ROW + t;      // and two independent butterflies in flight
+                const uint4 a = g[0], bq = g[4 * FUSED_ROW];
                 int o0[8], o1[8];
                 if (high_half) {
-                    const uint4 cq = g[8 * FUSED_TPB], dq = g[12 * FUSED_TPB];
+                    const uint4 cq = g[8 * FUSED_ROW], dq = g[12 * FUSED_ROW];
                     idct8<18>((int)a.x, (int)a.y, (int)bq.x, (int)bq.y, (int)cq.x, (int)cq.y, (int)dq.x, (int)dq.y, o0);
                     idct8<18>((int)a.z, (int)a.w, (int)bq.z, (int)bq.w, (int)cq.z, (int)cq.w, (int)dq.z, (int)dq.w, o1);
                 } else {
