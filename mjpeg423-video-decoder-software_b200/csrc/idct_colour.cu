@@ -95,6 +95,10 @@ k_colour(const uint8_t* __restrict__ samples, uint8_t* __restrict__ out, uint32_
 }
 
 // ---- fused IDCT + colour: coefficient planes (frame-major, Y|Cb|Cr) -> BGRA raster ------------------
+// One plane at a time: the thread's block goes through the register IDCT and its 64 samples are written back over the
+// first half of the block's own (already consumed) coefficient slot; the colour conversion then reads the three sample
+// blocks back row by row.  (Keeping all three planes' samples in registers took 128 registers and ran at 20 % of the
+// warp slots and 41 % of the HBM peak, profiles/r02a; this form needs about as many as k_idct.)
 __global__ void __launch_bounds__(IDCT_TPB, 4)
 k_idct_colour(const int16_t* __restrict__ coef, uint8_t* __restrict__ out, uint32_t nb, uint32_t wb, uint32_t W, uint32_t groups) {
     extern __shared__ __align__(128) uint8_t smem[];          // 3 x TILE_BYTES
@@ -108,25 +112,35 @@ k_idct_colour(const int16_t* __restrict__ coef, uint8_t* __restrict__ out, uint3
     cp_async_wait_all();
     __syncthreads();
     const bool live = t < nblk;
-    uint32_t px[3][16];
-#pragma unroll
+#pragma unroll 1
     for (int p = 0; p < 3; p++) {
+        uint8_t* tile = smem + p * TILE_BYTES;
         uint4 rows[8];
         uint32_t ac = 0, any = 0;
-        if (live) { load_block_rows(smem + p * TILE_BYTES, t, rows); block_masks(rows, ac, any); }
+        if (live) { load_block_rows(tile, t, rows); block_masks(rows, ac, any); }
         else {
 #pragma unroll
             for (int r = 0; r < 8; r++) rows[r] = make_uint4(0, 0, 0, 0);
         }
-        idct_block(rows, warp_or(ac), warp_or(any), px[p]);
+        uint32_t px[16];
+        idct_block(rows, warp_or(ac), warp_or(any), px);
+        // samples of row pair k (rows 2k, 2k+1) -> chunk k of the thread's slot (same swizzle as the coefficients: the
+        // slot is the thread's own, and all eight of its coefficient chunks are in registers by now)
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            *reinterpret_cast<uint4*>(tile + t * 128 + ((k ^ (t & 7)) << 4)) = make_uint4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
     }
     if (!live) return;
     const uint32_t b = b0 + (uint32_t)t;
     uint8_t* dst = out + ((size_t)f * nb * 64 + ((size_t)(b / wb) * 8 * W + (size_t)(b % wb) * 8)) * 4;
 #pragma unroll
-    for (int r = 0; r < 8; r++)
-        colour_row_store(px[0][2 * r], px[0][2 * r + 1], px[1][2 * r], px[1][2 * r + 1], px[2][2 * r], px[2][2 * r + 1],
-                         dst + (size_t)r * W * 4);
+    for (int k = 0; k < 4; k++) {
+        const uint32_t off = t * 128 + ((k ^ (t & 7)) << 4);
+        const uint4 y = *reinterpret_cast<const uint4*>(smem + off), cb = *reinterpret_cast<const uint4*>(smem + TILE_BYTES + off),
+                    cr = *reinterpret_cast<const uint4*>(smem + 2 * TILE_BYTES + off);
+        colour_row_store(y.x, y.y, cb.x, cb.y, cr.x, cr.y, dst + (size_t)(2 * k) * W * 4);
+        colour_row_store(y.z, y.w, cb.z, cb.w, cr.z, cr.w, dst + (size_t)(2 * k + 1) * W * 4);
+    }
 }
 
 // ---- position-mixed 64-bit checksum of each frame (bench: whole-batch bit-exactness) ----------------
