@@ -102,9 +102,10 @@ def test_header_is_c99_and_example_links(tmp_path, lib):
         pytest.skip("gcc not available")
     exe = tmp_path / "decode_file"
     pkg = os.path.join(ROOT, "mjpeg423-video-decoder-software_b200")
-    cmd = ["gcc", "-std=c99", "-pedantic-errors", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "examples", "decode_file.c"), "-L", pkg, "-lmjpeg423_b200", f"-Wl,-rpath,{pkg}", "-o", str(exe)]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    assert res.returncode == 0, res.stderr
-    out = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert out.returncode == 2 and "usage" in out.stderr
+    for src in ("decode_file.c", "seek_and_shard.c"):
+        cmd = ["gcc", "-std=c99", "-pedantic-errors", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+               os.path.join(ROOT, "examples", src), "-L", pkg, "-lmjpeg423_b200", f"-Wl,-rpath,{pkg}", "-o", str(exe)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        out = subprocess.run([str(exe)], capture_output=True, text=True)
+        assert out.returncode == 2 and "usage" in out.stderr
